@@ -1,0 +1,160 @@
+/*
+ * include/marlnav_b200.h -- C ABI of libmarlnav_b200.so
+ *
+ * Drop-in boundary for ONE path of JussiM01/MARL-nav: the batched environment
+ * step, marlnav/environment.py (Env.__init__ :11-68, Env.step :92-107,
+ * Env.observations :139-180).  The reference has no FFI of its own -- the seam
+ * is the duck-typed Python class `Env` -- so these entry
+ * points are what a ctypes binding of that class needs and nothing more; the
+ * binding itself is marlnav_b200/env.py and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Every `float*` / `uint8_t*` / `unsigned long long*` below is a DEVICE
+ *     pointer into caller-owned memory unless the name ends in `_host`.
+ *   - Tensors use the reference's layouts, contiguous, float32:
+ *       states (B,A,5) = [x, y, dir_x, dir_y, speed]     environment.py:28, utils.py:386
+ *       obstacles (B,O,2), target (B,1,2)                 environment.py:29-30
+ *       actions (B,A,2) = [turn angle rad, acceleration]  environment.py:115-119
+ *       obs (B,A,S), S = 2 + 2*O + 2*(A-1), field order of the reference's
+ *         `Observations` namedtuple (utils.py:13-15):
+ *         [target_angle | target_distance | obstacles_angles(O) |
+ *          obstacles_distances(O) | others_angles(A-1) | others_distances(A-1)]
+ *       step_num (B) float32 (environment.py:38), terminates (B) 1-byte bool
+ *       (environment.py:39), rewards (B), terminated/truncated (B) 1-byte bool.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All calls are asynchronous on that stream; none allocates or synchronises
+ *     (the *_host variants enqueue copies; the caller synchronises).
+ *   - Return value: 0 on success, a cudaError_t (>0) for a CUDA failure,
+ *     <0 for an argument error; marlnav_last_error() describes the last failure
+ *     of the calling thread.
+ *   - There is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef MARLNAV_B200_H
+#define MARLNAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARLNAV_ABI_VERSION 1
+#define MARLNAV_MAX_AGENTS 26     /* torch.cdist's direct formula holds up to 25 columns */
+#define MARLNAV_MAX_OBSTACLES 64
+
+#define MARLNAV_ERR_BAD_ARG   (-1)
+#define MARLNAV_ERR_BAD_SHAPE (-2)
+#define MARLNAV_ERR_ALIGN     (-3)
+
+/* Everything Env.__init__ reads from params (environment.py:13-19,32-35,48-53) plus
+ * the geometry constants it hard-codes (environment.py:56-68) and the obstacle box
+ * of TriangleIntitializer (utils.py:344-347).  Passed by pointer, read on the host. */
+typedef struct marlnav_env_params {
+    int32_t num_envs;        /* B = num_parallel (this process's slice) */
+    int32_t num_agents;      /* A, 2..MARLNAV_MAX_AGENTS */
+    int32_t num_obstacles;   /* O, 1..MARLNAV_MAX_OBSTACLES */
+    int32_t episode_len;     /* truncated = step_num > episode_len - 1 */
+    float min_speed, max_speed, min_accel, max_accel;
+    float risk_factor, distance_factor, heading_factor, target_factor, soft_factor, bond_factor;
+    float ob_risk_dist, ag_risk_dist, ob_coll_dist, ag_coll_dist;
+    float agents_min_d, agents_max_d, max_at_prop_d, max_angle_diff;
+    float target_radius, cap_distance, bond_sharpness, ideal_dist, init_dist;
+    float obst_x_range, obst_x_mean, obst_y_range, obst_y_mean;
+} marlnav_env_params;
+
+/* Where re-initialised envs get their state (Env._reinit, environment.py:76-90).
+ *   env stride 0  -> one template shared by all envs (TriangleIntitializer's
+ *                    constant agents/target, utils.py:349-368)
+ *   env stride >0 -> per-env templates (MockInitializer, utils.py:310-319)
+ *   tmpl_obstacles == NULL -> obstacles re-sampled uniformly in the box with
+ *                    Philox4x32-10 addressed by (seed; global env id,
+ *                    step_counter, obstacle pair) -- replaces the global
+ *                    mt19937 draw of utils.py:390-398.
+ *   alias_first_step != 0 -> reproduce MockInitializer's aliasing on the first
+ *                    step: the template IS the current state. */
+typedef struct marlnav_reset_spec {
+    const float* tmpl_states;
+    const float* tmpl_obstacles;
+    const float* tmpl_target;
+    int64_t states_env_stride, obstacles_env_stride, target_env_stride;   /* in floats */
+    int32_t alias_first_step;
+    int32_t reserved;
+    uint64_t seed;
+    uint64_t step_counter;     /* 0 at construction, k for the k-th step() call */
+    uint64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */
+} marlnav_reset_spec;
+
+/* Optional fused caller-side transforms:
+ *   ObsNormalizer  utils.py:519-532   obs_norm[k] = (obs[k] - mean[k]) / scale[k]
+ *   ActionScaler   utils.py:535-547   action[k]   = scale[k] * raw[k] + mean[k]
+ * All pointers device; NULL disables the corresponding transform. */
+typedef struct marlnav_io_transform {
+    const float* obs_mean;     /* (S) */
+    const float* obs_scale;    /* (S) */
+    const float* act_mean;     /* (2) */
+    const float* act_scale;    /* (2) */
+} marlnav_io_transform;
+
+int         marlnav_abi_version(void);
+const char* marlnav_last_error(void);
+/* S = 2 + 2*O + 2*(A-1); 0 for invalid (A,O). */
+int         marlnav_obs_size(int num_agents, int num_obstacles);
+/* Number of CUDA devices visible (0 when there is none / no driver). */
+int         marlnav_device_count(void);
+
+/* Env.__init__'s first `self._init_sampler()` + counters (environment.py:26-40):
+ * fills states/obstacles/target from `reset` (step_counter is used as given,
+ * normally 0) and zeroes step_num / terminates. */
+int marlnav_init_f32(const marlnav_env_params* params, const marlnav_reset_spec* reset,
+                     float* states, float* obstacles, float* target,
+                     float* step_num, uint8_t* terminates, void* stream);
+
+/* Env.observations() (environment.py:139-180): obs <- f(states, obstacles, target). */
+int marlnav_observe_f32(const marlnav_env_params* params,
+                        const float* states, const float* obstacles, const float* target,
+                        float* obs, void* stream);
+
+/* Env.step(actions) (environment.py:92-107) as ONE kernel launch:
+ * move -> count -> observe -> rewards/terminal flags -> episode stats ->
+ * masked re-initialisation -> observe again (returned obs are post-reset).
+ *   in-out: states, obstacles, target, step_num, terminates
+ *   out   : obs (B,A,S), rewards (B), terminated (B), truncated (B)
+ *   stats : device uint64[3], += (num_trunc, num_col, num_tar)  environment.py:98,210,211
+ *   io    : may be NULL.  With io->act_* set, `actions` are the policy's raw
+ *           [-1,1] outputs; with io->obs_* set, `obs` receives normalised values. */
+int marlnav_step_f32(const marlnav_env_params* params, const marlnav_reset_spec* reset,
+                     float* states, float* obstacles, float* target,
+                     float* step_num, uint8_t* terminates,
+                     const float* actions,
+                     float* obs, float* rewards, uint8_t* terminated, uint8_t* truncated,
+                     unsigned long long* stats,
+                     const marlnav_io_transform* io, void* stream);
+
+/* Same step for a HOST-resident policy: `actions_host` is copied H2D, the step
+ * runs, and obs/rewards/flags are copied D2H, all enqueued on `stream`.  Host
+ * buffers should be pinned for the copies to be asynchronous.  `actions_dev`,
+ * `obs_dev`, `rewards_dev`, `terminated_dev`, `truncated_dev` are device staging
+ * buffers of the usual shapes owned by the caller.  Environment state stays on
+ * the device (it never leaves HBM between steps). */
+int marlnav_step_host_f32(const marlnav_env_params* params, const marlnav_reset_spec* reset,
+                          float* states, float* obstacles, float* target,
+                          float* step_num, uint8_t* terminates,
+                          const float* actions_host, float* actions_dev,
+                          float* obs_dev, float* rewards_dev,
+                          uint8_t* terminated_dev, uint8_t* truncated_dev,
+                          float* obs_host, float* rewards_host,
+                          uint8_t* terminated_host, uint8_t* truncated_host,
+                          unsigned long long* stats,
+                          const marlnav_io_transform* io, void* stream);
+
+/* Launch geometry the library would use for (A,O,B): for bench/roofline reporting.
+ * Writes grid, block, dynamic smem bytes, envs per CTA; returns 0 or an error. */
+int marlnav_step_launch_info(const marlnav_env_params* params,
+                             int* grid, int* block, int* smem_bytes, int* envs_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLNAV_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of libmarlnav_b200.so (C ABI: include/marlnav_b200.h).
+
+There is no CPU fallback and no JIT: the shared library must have been built
+in-tree (``python -m marlnav_b200.build``); loading fails loudly otherwise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmarlnav_b200.so")
+
+ABI_VERSION = 1
+
+# every symbol include/marlnav_b200.h declares
+EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",
+           "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
+           "marlnav_step_launch_info")
+
+
+class EnvParams(ctypes.Structure):
+    """struct marlnav_env_params"""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("num_envs", "num_agents", "num_obstacles", "episode_len")] + \
+               [(n, ctypes.c_float) for n in (
+                   "min_speed", "max_speed", "min_accel", "max_accel",
+                   "risk_factor", "distance_factor", "heading_factor", "target_factor",
+                   "soft_factor", "bond_factor",
+                   "ob_risk_dist", "ag_risk_dist", "ob_coll_dist", "ag_coll_dist",
+                   "agents_min_d", "agents_max_d", "max_at_prop_d", "max_angle_diff",
+                   "target_radius", "cap_distance", "bond_sharpness", "ideal_dist", "init_dist",
+                   "obst_x_range", "obst_x_mean", "obst_y_range", "obst_y_mean")]
+
+
+class ResetSpec(ctypes.Structure):
+    """struct marlnav_reset_spec"""
+    _fields_ = [("tmpl_states", ctypes.c_void_p), ("tmpl_obstacles", ctypes.c_void_p),
+                ("tmpl_target", ctypes.c_void_p),
+                ("states_env_stride", ctypes.c_int64), ("obstacles_env_stride", ctypes.c_int64),
+                ("target_env_stride", ctypes.c_int64),
+                ("alias_first_step", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
+                ("env_id_offset", ctypes.c_uint64)]
+
+
+class IoTransform(ctypes.Structure):
+    """struct marlnav_io_transform"""
+    _fields_ = [("obs_mean", ctypes.c_void_p), ("obs_scale", ctypes.c_void_p),
+                ("act_mean", ctypes.c_void_p), ("act_scale", ctypes.c_void_p)]
+
+
+class MarlnavError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MarlnavError(
+            f"{LIB_PATH} is missing. Build it with `python -m marlnav_b200.build` "
+            "(nvcc, sm_100a). marlnav_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.marlnav_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        if name != "marlnav_last_error":
+            getattr(lib, name).restype = ctypes.c_int
+    got = lib.marlnav_abi_version()
+    if got != ABI_VERSION:
+        raise MarlnavError(f"libmarlnav_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().marlnav_last_error().decode(errors="replace")
+        raise MarlnavError(f"{what} failed (code {rc}): {msg}")
