@@ -18,7 +18,7 @@ LIB = os.path.join(_HERE, "libmarlnav_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-mfma,-ffp-contract=off", "-shared", "-cudart", "static"]
 
 
 def nvcc_path():

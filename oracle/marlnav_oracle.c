@@ -19,12 +19,14 @@
  *   obstacle box sampling utils.py:390-398      _sample_obstacles (RNG replaced, see below)
  *
  * Two deliberate, documented substitutions (DESIGN.md "Oracle"):
- *   1. cos/sin/acos use torch_cpu_math.h (SLEEF u10, bit-verified against the
- *      SLEEF symbols inside libtorch_cpu.so).  torch's MKL build routes these
- *      three ops through closed-source MKL VML, which differs from SLEEF by
- *      <= 1 ulp on ~2-9 % of inputs; golden vectors are therefore produced
- *      twice (stock torch -> tolerance tests, SLEEF-patched torch -> bit-exact
- *      tests), see tests/golden/make_golden.py.
+ *   1. cos/sin/acos use marlnav_trig.h (IEEE-only fp32 algorithms, max error
+ *      1.38 / 1.48 / 1.12 ulp, exhaustively measured).  torch's MKL build routes
+ *      these three ops through closed-source MKL VML, which cannot be restated;
+ *      it differs even from torch's own other backend (SLEEF u10, restated in
+ *      torch_cpu_math.h) by 1 ulp on 2-9 % of inputs.  Golden vectors are
+ *      therefore produced twice (stock torch -> tolerance tests; torch with
+ *      sin/cos/acos patched to marlnav_trig -> bit-exact tests), see
+ *      tests/golden/make_golden.py.
  *   2. The reference re-samples obstacles from the global CPU mt19937 stream
  *      for the whole batch every step (utils.py:382-394).  Resets here draw
  *      from an addressed Philox4x32-10 stream; the same
@@ -39,7 +41,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "torch_cpu_math.h"
+#include "marlnav_trig.h"
+#include "torch_cpu_math.h"   /* SLEEF-u10 restatement: kept for mo_trig_sleef (comparison only) */
 
 #define MO_MAX_AGENTS 26      /* torch.cdist leaves the direct formula above 25 columns */
 #define MO_MAX_OBSTACLES 64
@@ -167,7 +170,8 @@ static inline float mo_clampf(float x, float lo, float hi) {
 static void mo_move_agent(const mo_params* p, float* s /* [x,y,dx,dy,v] */, const float* a) {
     const float PI_F = 3.1415927410125732f;
     float th = mo_clampf(a[0], -PI_F, PI_F);
-    float c = tcm_cosf(th), sn = tcm_sinf(th);
+    float c, sn;
+    mt_sincosf(th, &sn, &c);
     float dx = s[2], dy = s[3];
     float ndx = (c * dx) + ((-sn) * dy);
     float ndy = (sn * dx) + (c * dy);
@@ -190,7 +194,7 @@ static inline void mo_pair(const mo_params* p, float ox, float oy, float hx, flo
     float dot = mo_clampf((hx * nx) + (hy * ny), -1.0f, 1.0f);
     float orthx = nx - (dot * hx);
     float sign = orthx > 0.0f ? -1.0f : 1.0f;
-    float ang = sign * tcm_acosf(dot);
+    float ang = sign * mt_acosf(dot);
     if (d < p->cap_distance) ang = 0.0f;
     *angle = ang; *dist = d;
 }
@@ -367,7 +371,18 @@ void mo_triangle_template(float ags_dist, float cx, float cy, float speed, float
     }
 }
 
+/* the oracle's own sin(0)/cos(1)/acos(2) on arrays -- used to patch torch.sin/cos/acos
+ * when goldens are generated from the real reference (tests/golden/refload.py) */
 void mo_trig(int which, const float* x, float* y, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        float s, c;
+        if (which == 2) { y[i] = mt_acosf(x[i]); continue; }
+        mt_sincosf(x[i], &s, &c);
+        y[i] = which == 0 ? s : c;
+    }
+}
+/* SLEEF u10 (torch's non-MKL CPU backend), for accuracy comparisons only */
+void mo_trig_sleef(int which, const float* x, float* y, size_t n) {
     for (size_t i = 0; i < n; ++i)
         y[i] = which == 0 ? tcm_sinf(x[i]) : which == 1 ? tcm_cosf(x[i]) : tcm_acosf(x[i]);
 }

@@ -1,0 +1,78 @@
+/*
+ * oracle/marlnav_trig.h -- TEST INFRASTRUCTURE (oracle), not product code.
+ *
+ * The float32 sin/cos/acos the oracle (and, operation for operation, the CUDA
+ * kernel in marlnav_b200/csrc/marlnav_math.cuh) use for
+ *   torch.cos / torch.sin   /root/reference/marlnav/environment.py:134-135
+ *   torch.acos              /root/reference/marlnav/environment.py:286
+ *
+ * Why not "what torch does": on the MKL builds of torch used here the three ops
+ * run in closed-source MKL VML (vsCos/vsSin/vsAcos, high-accuracy mode); there
+ * is no published algorithm to restate and its bits differ from torch's other
+ * CPU backend (SLEEF u10, restated bit-exactly in torch_cpu_math.h) on 2-9 % of
+ * inputs by 1 ulp.  Any faithful implementation is therefore "as close to the
+ * reference as the reference is to itself across builds".  The functions below
+ * are built ONLY from IEEE-754 correctly-rounded operations (+ - * fma sqrt), so
+ * C on the host and CUDA on the device produce identical bits, and they are
+ * cheap on the device (the step is instruction-issue bound).
+ *
+ * Accuracy (oracle/verify_math_exhaustive.py, every float32 in the domain,
+ * against the correctly rounded result): see DESIGN.md "Transcendentals".
+ *
+ *   mt_sincosf(t): |t| <= pi (the step clamps turn angles first).  Cody-Waite
+ *       reduction by pi/2 (k in -2..2, two-term split, fused), cephes-style
+ *       minimax polynomials on [-pi/4, pi/4], quadrant fix-up.
+ *   mt_acosf(x):   |x| <= 1.  asin polynomial on z in [0, 1/4] (the degree-4
+ *       minimax set also used by SLEEF's asinf/acosf):
+ *         |x| <= .5 : pi/2 - asin(x)          asin(x) = x + x*z*P(z), z = x*x
+ *         |x| >  .5 : 2*asin(sqrt(z)), z=(1-|x|)/2   (pi - that for x < 0)
+ *       (1-|x|) is exact there, so small angles keep full relative accuracy.
+ *
+ * Compile with -ffp-contract=off: only the explicit fmaf() calls may fuse.
+ */
+#ifndef MARLNAV_ORACLE_TRIG_H
+#define MARLNAV_ORACLE_TRIG_H
+
+#include <math.h>
+
+#define MT_2_PI    0.636619746685028076171875f      /* RN(2/pi) */
+#define MT_PIO2_HI 1.57079637050628662109375f       /* RN(pi/2) */
+#define MT_PIO2_LO -4.37113882867379114031791687e-8f /* RN(pi/2 - MT_PIO2_HI) */
+#define MT_PI_HI   3.1415927410125732421875f        /* RN(pi) */
+#define MT_PI_LO   -8.74227765734758228063583374e-8f /* RN(pi - MT_PI_HI) */
+
+static inline void mt_sincosf(float t, float* sn, float* cs) {
+    const float k = rintf(t * MT_2_PI);
+    float r = fmaf(k, -MT_PIO2_HI, t);
+    r = fmaf(k, -MT_PIO2_LO, r);
+    const float z = r * r;
+    float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float s = (t == 0.0f) ? t : fmaf(r * z, ps, r);   /* keeps sin(-0) = -0 like torch */
+    float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    const float c = fmaf(z, fmaf(z, pc, -0.5f), 1.0f);
+    const int q = (int)k & 3;                        /* two's complement: -1 -> 3, -2 -> 2 */
+    const float s1 = (q & 1) ? c : s;
+    const float c1 = (q & 1) ? s : c;
+    *sn = (q & 2) ? -s1 : s1;
+    *cs = ((q + 1) & 2) ? -c1 : c1;
+}
+
+static inline float mt_acosf(float x) {
+    const float a = fabsf(x);
+    const int small = a <= 0.5f;
+    const float z = small ? (x * x) : ((1.0f - a) * 0.5f);
+    const float t = small ? x : sqrtf(z);
+    float u = +0.4197454825e-1f;
+    u = fmaf(u, z, +0.2424046025e-1f);
+    u = fmaf(u, z, +0.4547423869e-1f);
+    u = fmaf(u, z, +0.7495029271e-1f);
+    u = fmaf(u, z, +0.1666677296e+0f);
+    const float as = fmaf(t * z, u, t);              /* asin(t) */
+    if (small) return MT_PIO2_HI - (as - MT_PIO2_LO);
+    const float twice = as + as;
+    return x < 0.0f ? (MT_PI_HI - (twice - MT_PI_LO)) : twice;
+}
+
+#endif

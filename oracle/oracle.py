@@ -8,7 +8,7 @@ Python face of the CPU oracle for MARL-nav's batched environment step
 Three things live here:
 
 * ``OracleEnv``      -- ctypes wrapper over ``libmarlnav_oracle.so``
-                        (``marlnav_oracle.c``: plain C, SLEEF-u10 trig, Philox
+                        (``marlnav_oracle.c``: plain C, marlnav_trig.h trig, Philox
                         resets).  The CUDA path must match it bit for bit.
 * ``TorchPortEnv``   -- the same step restated with the reference's own torch
                         op sequence (cdist / normalize / einsum / vmap-free 2x2
@@ -72,7 +72,7 @@ class MoReset(ctypes.Structure):
 def build(force: bool = False) -> str:
     """Compile marlnav_oracle.c with oracle/Makefile (gcc; seconds)."""
     src_m = max(os.path.getmtime(os.path.join(_HERE, f))
-                for f in ("marlnav_oracle.c", "torch_cpu_math.h", "Makefile"))
+                for f in ("marlnav_oracle.c", "torch_cpu_math.h", "marlnav_trig.h", "Makefile"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
         subprocess.run(["make", "-C", _HERE, "-B", "libmarlnav_oracle.so"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)

@@ -4,8 +4,8 @@ skip when the reference is absent (it never travels to the GPU box).
 
 * matplotlib / PyQt5 are not installed, and marlnav/utils.py:3, models.py:5,
   animation.py:1,7 import matplotlib at module top -> stub modules.
-* ``sleef_trig()`` swaps ``torch.cos/sin/acos`` for custom ops backed by the C
-  oracle's SLEEF-u10 restatement (with vmap rules, because the reference calls
+* ``oracle_trig()`` swaps ``torch.cos/sin/acos`` for custom ops backed by the C
+  oracle's own trig (oracle/marlnav_trig.h; with vmap rules, because the reference calls
   cos/sin under ``vmap(vmap(...))``, environment.py:128-135).  That is the one
   substitution behind the "bit-exact" golden set: every other torch op the
   reference executes is stock.
@@ -69,7 +69,7 @@ def _define_ops():
 
 
 @contextlib.contextmanager
-def sleef_trig():
+def oracle_trig():
     trig = _define_ops()
     saved = (torch.sin, torch.cos, torch.acos)
     torch.sin = lambda x: trig(x, 0)
