@@ -117,3 +117,54 @@ def test_sharded_equals_single(oracle):
     assert torch.equal(e_full.obstacles, torch.cat([s.obstacles for s in shards]))
     tot = sum(s.episode_stats for s in shards)
     assert torch.equal(tot, e_full.episode_stats)
+
+
+def test_fused_normalizer_and_scaler(oracle):
+    """fuse_io(): ObsNormalizer (utils.py:519-532) and ActionScaler (utils.py:535-547) folded
+    into the kernel must equal applying them around the oracle step, bit for bit."""
+    import math
+    import marlnav_b200 as mb
+    B, A, O = 777, 3, 3
+    params = mb.default_env_params(B, A, O, sampling_style='policy')
+    env = _mk(params, 9)
+    oe = oracle.OracleEnv(cpu_params(params), seed=9)
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm = dict(min_obs=lo, max_obs=hi)
+    scal = dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    env.fuse_io(norm, scal)
+    lo_t, hi_t = torch.tensor(lo), torch.tensor(hi)
+    o_scale, o_mean = (0.5 * (hi_t - lo_t)).numpy(), (0.5 * (lo_t + hi_t)).numpy()
+    a_lo, a_hi = torch.tensor(scal['min_action']), torch.tensor(scal['max_action'])
+    a_scale, a_mean = (0.5 * (a_hi - a_lo)).numpy(), (0.5 * (a_lo + a_hi)).numpy()
+    g = torch.Generator().manual_seed(3)
+    for t in range(80):
+        raw = (torch.rand(B, A, 2, generator=g) * 2 - 1) * torch.tensor([0.08, 1.0])
+        obs, rew, term, trunc = env.step_fused(raw.cuda())
+        scaled = (a_scale * raw.numpy()).astype(np.float32) + a_mean
+        o_obs, o_rew, o_term, o_trunc = oe.step_fused(scaled)
+        want = ((o_obs - o_mean).astype(np.float32) / o_scale).astype(np.float32)
+        assert_bits_equal(f"step {t} normalised obs", obs.cpu().numpy(), want)
+        assert_bits_equal(f"step {t} rewards", rew.cpu().numpy(), o_rew)
+        assert_bits_equal(f"step {t} term", term.cpu().numpy(), o_term)
+    assert_bits_equal("states", env.states.cpu().numpy(), oe.states)
+
+
+def test_host_stepper_matches_device_step(oracle):
+    """marlnav_step_host_f32 (pinned host in/out) == the device-resident step."""
+    import marlnav_b200 as mb
+    params = mb.default_env_params(2048, 3, 3, sampling_style='policy')
+    e1, e2 = _mk(params, 4), _mk(params, 4)
+    hs = mb.HostStepper(e2)
+    pool = action_pool(2048, 3)
+    for t in range(40):
+        act = pool[t % len(pool)]
+        obs, rew, term, trunc = e1.step_fused(act.cuda())
+        hs.actions_host.copy_(act)
+        hs.step()
+        assert torch.equal(obs.cpu(), hs.obs_host)
+        assert torch.equal(rew.cpu(), hs.rewards_host)
+        assert torch.equal(term.cpu(), hs.terminated_host.bool())
+        assert torch.equal(trunc.cpu(), hs.truncated_host.bool())
+    assert torch.equal(e1.states, e2.states)
