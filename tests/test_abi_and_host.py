@@ -1,0 +1,157 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol (no compute calls),
+host-side parameter/sampler/sharding logic, world_size-2 gloo reduction of episode stats."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from marlnav_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "marlnav_b200.h")).read()
+    declared = set(re.findall(r"\b(marlnav_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.marlnav_abi_version() == 1
+    assert lib.marlnav_obs_size(3, 3) == 12 and lib.marlnav_obs_size(8, 16) == 48
+    assert lib.marlnav_obs_size(1, 3) == 0 and lib.marlnav_obs_size(3, 0) == 0
+    assert lib.marlnav_obs_size(27, 3) == 0
+
+
+def test_struct_layouts_match_header():
+    from marlnav_b200 import _lib
+    assert ctypes.sizeof(_lib.EnvParams) == 4 * 4 + 27 * 4
+    assert ctypes.sizeof(_lib.ResetSpec) == 3 * 8 + 3 * 8 + 8 + 3 * 8
+    assert ctypes.sizeof(_lib.IoTransform) == 4 * 8
+    from oracle import oracle as orc
+    assert ctypes.sizeof(orc.MoParams) == ctypes.sizeof(_lib.EnvParams)
+    assert [f[0] for f in orc.MoParams._fields_] == [f[0] for f in _lib.EnvParams._fields_]
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from marlnav_b200 import _lib
+    lib = _lib.load()
+    p = _lib.EnvParams(); p.num_envs, p.num_agents, p.num_obstacles = 4, 1, 3
+    rc = lib.marlnav_observe_f32(ctypes.byref(p), None, None, None, None, None)
+    assert rc == -2 and b"num_agents" in lib.marlnav_last_error()
+    p.num_agents = 3
+    rc = lib.marlnav_observe_f32(ctypes.byref(p), None, None, None, None, None)
+    assert rc == -1 and b"NULL" in lib.marlnav_last_error()
+    g, b, s, e = (ctypes.c_int() for _ in range(4))
+    p.num_envs = 1048576
+    assert lib.marlnav_step_launch_info(ctypes.byref(p), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s),
+                                        ctypes.byref(e)) == 0
+    assert g.value * e.value >= 1048576 and b.value % 32 == 0 and s.value < 227 * 1024
+
+
+def test_env_refuses_cpu_device():
+    import marlnav_b200 as mb
+    with pytest.raises(mb.MarlnavError, match="no CPU fallback"):
+        mb.Env(mb.default_env_params(device='cpu'))
+
+
+def test_default_params_mirror_reference_cli_defaults():
+    import marlnav_b200 as mb
+    p = mb.default_env_params()
+    assert (p['num_parallel'], p['num_agents'], p['num_obstacles'], p['episode_len']) == (2, 3, 3, 200)
+    assert (p['min_speed'], p['max_speed'], p['min_accel'], p['max_accel']) == (3., 10., -0.5, 0.5)
+    assert [p[k] for k in ('risk_factor', 'distance_factor', 'heading_factor', 'target_factor',
+                           'soft_factor', 'bond_factor')] == [0., 0., 500., 500., 500., 10.]
+    assert p['init']['init_method'] == 'triangle' and p['sampler']['sample_method'] == 'const_sampler'
+    p0 = mb.default_env_params(sampler_num=0)
+    assert p0['num_obstacles'] == 1 and p0['init']['mock_states'][0][2] == [950., 100., 0., 1., 5.]
+    assert mb.default_env_params(sampling_style='policy')['sampler'] is None
+
+
+def test_samplers_follow_reference_scripts():
+    import math
+    from marlnav_b200 import params as P
+    from marlnav_b200.samplers import action_sampler
+    c = action_sampler(dict(P.CONST_SAMPLER, num_parallel=4, num_agents=3, device='cpu'))
+    assert c().shape == (4, 3, 2) and torch.equal(c()[2, 1], torch.tensor([0., 1.]))
+    m0 = action_sampler(dict(P.MOCK_SAMPLER_0, max_step=3, device='cpu'))
+    assert torch.equal(m0()[1, 2], torch.tensor([0., -100.]))
+    m0(); m0()
+    with pytest.raises(StopIteration):
+        m0()
+    m1 = action_sampler(dict(P.MOCK_SAMPLER_1, max_step=5, device='cpu'))
+    first, second = m1(), m1()
+    assert torch.allclose(first[0, 0], torch.tensor([-math.pi / 6, 0.]))
+    assert torch.allclose(first[1, 0], torch.tensor([-0.5 * math.radians(1.8), 0.]))
+    assert torch.allclose(second[1, 2], torch.tensor([math.radians(1.8), 0.]))
+    assert torch.equal(second[0], torch.zeros(3, 2))
+    assert action_sampler(None) is None
+
+
+def test_shard_bounds_partition_exactly():
+    import marlnav_b200 as mb
+    for total, world in [(1048576, 8), (1000, 3), (7, 7), (10, 4)]:
+        spans = [mb.shard_bounds(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        mb.shard_bounds(10, 4, 4)
+
+
+def test_shard_env_params_offsets_and_scenarios():
+    import marlnav_b200 as mb
+    full = mb.default_env_params(1000, 3, 3, sampling_style='policy')
+    parts = [mb.shard_env_params(full, r, 3) for r in range(3)]
+    assert [p['num_parallel'] for p in parts] == [334, 333, 333]
+    assert [p['env_id_offset'] for p in parts] == [0, 334, 667]
+    assert full['num_parallel'] == 1000 and 'env_id_offset' not in full
+    mock = mb.shard_env_params(mb.default_env_params(sampler_num=1), 1, 2)
+    assert mock['num_parallel'] == 1 and len(mock['init']['mock_states']) == 1
+    assert mock['init']['mock_target'] == [[[750., 475.]]]
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import marlnav_b200 as mb
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+stats = torch.tensor([10 + rank, 200 * (rank + 1), 3000 - rank], dtype=torch.int64)
+tot = mb.reduce_episode_stats(stats.clone())
+assert tot.tolist() == [21, 600, 5999], tot
+off, cnt = mb.shard_bounds(1001, rank, 2)
+spans = [None, None]
+dist.all_gather_object(spans, (off, cnt))
+assert spans == [(0, 501), (501, 500)], spans
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_episode_stats_allreduce_gloo_world2(tmp_path):
+    """The only collective on the path: SUM of int64[3] episode counters (gloo on CPU here,
+    NCCL over NVLink on the GPU box)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_reduce_is_noop_without_process_group():
+    import marlnav_b200 as mb
+    s = torch.tensor([1, 2, 3], dtype=torch.int64)
+    assert mb.reduce_episode_stats(s).tolist() == [1, 2, 3]
+    with pytest.raises(ValueError):
+        mb.reduce_episode_stats(torch.zeros(3))
