@@ -222,6 +222,15 @@ static void mo_observe_env(const mo_params* p, const float* st, const float* ob,
     }
 }
 
+/* environment.py:113-137 on a whole batch (phase-split parity: move only) */
+void mo_move(const mo_params* p, float* states, const float* actions) {
+    const int A = p->num_agents;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < p->num_envs; ++b)
+        for (int i = 0; i < A; ++i)
+            mo_move_agent(p, states + ((size_t)b * A + i) * 5, actions + ((size_t)b * A + i) * 2);
+}
+
 void mo_observe(const mo_params* p, const float* states, const float* obstacles,
                 const float* target, float* obs) {
     const int A = p->num_agents, O = p->num_obstacles;

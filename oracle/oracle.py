@@ -248,6 +248,11 @@ class OracleEnv:
         self.terminates = np.zeros(B, np.uint8)
         self.stats = np.zeros(3, np.uint64)   # trunc, col, tar
 
+    def move_only(self, actions):
+        """environment.py:113-137 alone (in place on self.states) -- phase-split parity."""
+        actions = np.ascontiguousarray(actions, np.float32).reshape(self.B, self.A, 2)
+        lib().mo_move(ctypes.byref(self.p), _p(self.states), _p(actions))
+
     def observations_fused(self):
         obs = np.empty((self.B, self.A, self.S), np.float32)
         lib().mo_observe(ctypes.byref(self.p), _p(self.states), _p(self.obstacles),

@@ -1,0 +1,195 @@
+#!/usr/bin/env python
+"""tests/golden/make_golden.py -- generate the committed golden vectors by running the REAL
+reference (/root/reference/marlnav, unmodified, imported in the build container).
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+
+Two families (see DESIGN.md "Oracle and parity"):
+
+  patched_*.npz  The reference with exactly two substitutions injected from outside:
+                 (1) env._init_sampler := the addressed-Philox sampler of SURVEY.md
+                 Appendix D (same agent template / target, obstacle draws addressed by
+                 (seed, env id, call counter) instead of the global mt19937 stream);
+                 (2) torch.sin/cos/acos := oracle/marlnav_trig.h (the reference's own bits
+                 for these come from MKL VML, which cannot be restated).
+                 Every other torch op the reference executes is stock.  FREE-RUNNING
+                 traces; the C oracle and the CUDA kernel must reproduce them BIT FOR BIT.
+  stock_*.npz    The reference with stock torch trig (only the Philox sampler injected):
+                 per-step snapshots for teacher-forced tolerance tests (flags exact,
+                 floats 1e-5 where the arithmetic is well-conditioned).
+
+The reference's own `-rc -sn 0/1` scenarios (mock initialiser + scripted sampler) need no
+sampler injection at all: they are run through the reference's set_params() untouched.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refload                                   # noqa: E402  (also puts the repo root on sys.path)
+from oracle import oracle as orc                 # noqa: E402
+
+torch.set_num_threads(4)
+env_mod, utils_mod = refload.load()
+
+SNAP_EVERY = 20
+
+
+def actions_for(B, A, steps, seed, angle=0.2, accel=0.5):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(steps):
+        ang = (torch.rand(B, A, generator=g) * 2 - 1) * angle
+        acc = (torch.rand(B, A, generator=g) * 2 - 1) * accel
+        out.append(torch.stack([ang, acc], dim=2).contiguous())
+    return out
+
+
+def fused(obs):
+    return torch.cat(list(obs), dim=2).numpy().copy()
+
+
+def checksum(a):
+    return np.ascontiguousarray(a).view(np.uint32).astype(np.uint64).sum()
+
+
+def make_env(B, A, O, seed, template=None, **over):
+    """Reference Env built through the reference's own set_params, Philox sampler injected."""
+    args = refload.reference_args(num_parallel=B, num_agents=A, num_obstacles=O, **over)
+    params = copy.deepcopy(utils_mod.set_params(args)['env'])
+    env = env_mod.Env(params)
+    tmpl = orc.triangle_template(params['init']) if template is None else np.asarray(template, np.float32)
+    smp = orc.PhiloxTemplateSampler(params, tmpl, seed=seed)
+    env._init_sampler = smp
+    env.states, env.obstacles, env.target = smp()        # call 0 = construction-time sample
+    return env
+
+
+def run_trace(env, actions, record_pre=False):
+    """Free-running trace of a reference Env.  Returns dict of arrays."""
+    T = len(actions)
+    B = env.num_parallel
+    rec = dict(rewards=np.empty((T, B), np.float32), terminated=np.empty((T, B), bool),
+               truncated=np.empty((T, B), bool), obs_sum=np.empty(T, np.uint64),
+               states_sum=np.empty(T, np.uint64), snap_steps=[], snap_states=[], snap_obstacles=[],
+               snap_obs=[], snap_step_num=[], snap_terminates=[])
+    pre = dict(states=[], obstacles=[], target=[], step_num=[], terminates=[]) if record_pre else None
+    for t, act in enumerate(actions):
+        if record_pre and t % 4 == 0:
+            pre['states'].append(env.states.numpy().copy()); pre['obstacles'].append(env.obstacles.numpy().copy())
+            pre['target'].append(env.target.numpy().copy()); pre['step_num'].append(env._step_num.numpy().copy())
+            pre['terminates'].append(env._terminates.numpy().copy())
+        obs, rew, term, trunc = env.step(act.clone())
+        o = fused(obs)
+        rec['rewards'][t], rec['terminated'][t], rec['truncated'][t] = rew.numpy(), term.numpy(), trunc.numpy()
+        rec['obs_sum'][t], rec['states_sum'][t] = checksum(o), checksum(env.states.numpy())
+        if t % SNAP_EVERY == 0 or t == T - 1 or (record_pre and t % 4 == 0):
+            rec['snap_steps'].append(t); rec['snap_states'].append(env.states.numpy().copy())
+            rec['snap_obstacles'].append(env.obstacles.numpy().copy()); rec['snap_obs'].append(o)
+            rec['snap_step_num'].append(env._step_num.numpy().copy())
+            rec['snap_terminates'].append(env._terminates.numpy().copy())
+    out = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in rec.items()}
+    out['stats'] = np.array([env._num_trunc, env._num_col, env._num_tar], np.int64)
+    if record_pre:
+        for k, v in pre.items():
+            out['pre_' + k] = np.stack(v)
+    return out
+
+
+def save(name, meta, arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **{'meta_' + k: np.asarray(v) for k, v in meta.items()}, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, stats {arrays.get('stats')}")
+
+
+def random_case(name, B, A, O, steps, seed, act_seed, patched, template=None, angle=0.2, **over):
+    acts = actions_for(B, A, steps, act_seed, angle=angle)
+    ctx = refload.oracle_trig() if patched else torch.no_grad()
+    with ctx:
+        env = make_env(B, A, O, seed, template, **over)
+        init = dict(init_states=env.states.numpy().copy(), init_obstacles=env.obstacles.numpy().copy(),
+                    init_obs=fused(env.observations()))
+        arr = run_trace(env, acts, record_pre=not patched)
+    arr.update(init)
+    arr['actions'] = np.stack([a.numpy() for a in acts])
+    meta = dict(B=B, A=A, O=O, steps=steps, seed=seed, act_seed=act_seed, angle=angle,
+                episode_len=over.get('episode_len', 200))
+    if template is not None:
+        meta['template'] = np.asarray(template, np.float32)
+    save(name, meta, arr)
+
+
+def scenario_case(name, sn, patched):
+    """`python -m marlnav -rc -sn {0,1}`: reference initialiser + reference sampler, untouched."""
+    args = refload.reference_args(sampler_num=sn, num_obstacles=1)
+    ctx = refload.oracle_trig() if patched else torch.no_grad()
+    with ctx:
+        params = copy.deepcopy(utils_mod.set_params(args)['env'])
+        env = env_mod.Env(params)
+        acts = []
+
+        class Tap:          # record what the reference sampler hands out
+            def __init__(self, inner): self.inner = inner
+            def __call__(self):
+                a = self.inner(); acts.append(a.numpy().copy()); return a
+        env._sampler = Tap(env._sampler)
+        T = 1000
+        rec = dict(rewards=np.empty((T, 2), np.float32), terminated=np.empty((T, 2), bool),
+                   truncated=np.empty((T, 2), bool), obs_sum=np.empty(T, np.uint64), obs_e0a0=np.empty((T, 8), np.float32))
+        snaps = {}
+        for t in range(T):
+            obs, rew, term, trunc = env.step(env.sample_actions())
+            o = fused(obs)
+            rec['rewards'][t], rec['terminated'][t], rec['truncated'][t] = rew.numpy(), term.numpy(), trunc.numpy()
+            rec['obs_sum'][t] = checksum(o); rec['obs_e0a0'][t] = o[0, 0]
+            if t in (0, 1, 199, 200, 999):
+                snaps[f'states_{t}'] = env.states.numpy().copy(); snaps[f'obs_{t}'] = o
+        rec.update(snaps)
+        rec['stats'] = np.array([env._num_trunc, env._num_col, env._num_tar], np.int64)
+        rec['actions'] = np.stack(acts)
+    save(name, dict(sn=sn, steps=1000), rec)
+
+
+def quirk_case(name):
+    """delayed target termination, collision+target,
+    truncation -- 4 hand-placed envs, stock reference, constant action [0, -10]."""
+    B, A, O = 4, 3, 3
+    with refload.oracle_trig():
+        env = make_env(B, A, O, seed=0, episode_len=5)
+        env.obstacles[:] = 100.0
+        base = env.states.clone()
+        for e, dy in ((0, 10.0), (1, 3.0)):      # agents stacked near the target at (1350,375)
+            x = 1330.0 if e == 0 else 1340.0
+            for i, off in enumerate((0.0, dy, -dy)):
+                base[e, i] = torch.tensor([x, 375.0 + off, 1.0, 0.0, 3.0])
+        env.states = base
+        acts = [torch.tensor([0.0, -10.0]).repeat(B, A, 1) for _ in range(12)]
+        init = dict(init_states=env.states.numpy().copy(), init_obstacles=env.obstacles.numpy().copy())
+        arr = run_trace(env, acts)
+        # _terminates and step_num after every step are the point of these scenarios
+    arr.update(init)
+    arr['actions'] = np.stack([a.numpy() for a in acts])
+    save(name, dict(B=B, A=A, O=O, steps=12, seed=0, episode_len=5), arr)
+
+
+if __name__ == '__main__':
+    assert refload.available(), "the reference must be mounted at /root/reference"
+    random_case('patched_tri_3x3', 48, 3, 3, 260, seed=7, act_seed=1234, patched=True)
+    random_case('patched_tri_3x3_wide', 16, 3, 3, 60, seed=8, act_seed=99, patched=True, angle=4.0)
+    random_case('patched_ring_8x16', 12, 8, 16, 80, seed=5, act_seed=4321, patched=True,
+                template=orc.ring_template(8))
+    random_case('patched_ring_4x2', 16, 4, 2, 60, seed=3, act_seed=11, patched=True,
+                template=orc.ring_template(4))
+    random_case('patched_ring_9x5', 6, 9, 5, 40, seed=2, act_seed=12, patched=True,
+                template=orc.ring_template(9))
+    random_case('stock_tri_3x3', 48, 3, 3, 120, seed=7, act_seed=1234, patched=False)
+    random_case('stock_ring_8x16', 8, 8, 16, 40, seed=5, act_seed=4321, patched=False,
+                template=orc.ring_template(8))
+    for sn in (0, 1):
+        scenario_case(f'patched_rc_sn{sn}', sn, patched=True)
+        scenario_case(f'stock_rc_sn{sn}', sn, patched=False)
+    quirk_case('patched_quirks')
