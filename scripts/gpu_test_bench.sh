@@ -1,8 +1,8 @@
 # parity tests, then a plain bench line
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py --steps 500 --warmup 20 --cpu-budget 4 > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 300 python bench.py --steps 500 --warmup 20 --cpu-budget 4 > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err
 cat gpurun_out/bench_plain.json; tail -3 gpurun_out/bench_plain.err
-python bench.py --steps 200 --warmup 20 --no-cpu-baseline --agents 8 --obstacles 16 --envs 262144 > gpurun_out/bench_8x16.json 2>> gpurun_out/bench_plain.err
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --agents 8 --obstacles 16 --envs 262144 > gpurun_out/bench_8x16.json 2>> gpurun_out/bench_plain.err
 cat gpurun_out/bench_8x16.json
