@@ -58,8 +58,7 @@ def ncu_traffic(A, O, B):
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             t = json.load(f)
-        key = f"{B}x{A}x{O}"
-        return t.get(key)
+        return t.get(f"{B}x{A}x{O}")
     except Exception:
         return None
 
@@ -292,7 +291,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(A, O, B), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": algorithmic_bytes(A, O),
-                         "kernel": "mn::step_kernel", "per": "one launch = one step of one GPU's slice"},
+                         "kernel": "mn::step_warp_kernel" if A < 4 else "mn::step_kernel",
+                         "per": "one launch = one step of one GPU's slice"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes * world,
                     "d2h_bytes_per_step": hs.d2h_bytes * world, "steps": K2, "ms_per_step": ms_e2e / K2,
