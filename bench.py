@@ -139,6 +139,10 @@ def time_cpu_port(A, O, budget_s, steps=None, warmup=1, sample_envs=None):
     """Times oracle.TorchPortEnv (reference op sequence on torch CPU).  Returns
     (env_steps_per_s, cores, description, steps_done, ms_per_step)."""
     from oracle import oracle as orc
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core it may run on
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     B = sample_envs or 65536
     p = orc.default_env_params(B, A, O) if A == 3 else None
