@@ -74,13 +74,17 @@ typedef struct marlnav_env_params {
  *                    mt19937 draw of utils.py:390-398.
  *   alias_first_step != 0 -> reproduce MockInitializer's aliasing on the first
  *                    step: the template IS the current state. */
+/* flags: no element of a SHARED tmpl_states (states_env_stride == 0) has its sign bit set,
+ * so 0*template == +0 and the blend of a not-reset env reduces to old + 0 (no template reads) */
+#define MARLNAV_RESET_TMPL_NONNEG 1
+
 typedef struct marlnav_reset_spec {
     const float* tmpl_states;
     const float* tmpl_obstacles;
     const float* tmpl_target;
     int64_t states_env_stride, obstacles_env_stride, target_env_stride;   /* in floats */
     int32_t alias_first_step;
-    int32_t reserved;
+    int32_t flags;             /* MARLNAV_RESET_* bits */
     uint64_t seed;
     uint64_t step_counter;     /* 0 at construction, k for the k-th step() call */
     uint64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */

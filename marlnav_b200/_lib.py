@@ -37,7 +37,7 @@ class ResetSpec(ctypes.Structure):
                 ("tmpl_target", ctypes.c_void_p),
                 ("states_env_stride", ctypes.c_int64), ("obstacles_env_stride", ctypes.c_int64),
                 ("target_env_stride", ctypes.c_int64),
-                ("alias_first_step", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("alias_first_step", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
                 ("env_id_offset", ctypes.c_uint64)]
 
@@ -69,6 +69,12 @@ def load():
     for name in EXPORTS:
         if name != "marlnav_last_error":
             getattr(lib, name).restype = ctypes.c_int
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    lib.marlnav_step_f32.argtypes = [vp] * 15
+    lib.marlnav_observe_f32.argtypes = [vp] * 6
+    lib.marlnav_init_f32.argtypes = [vp] * 8
+    lib.marlnav_step_host_f32.argtypes = [vp] * 20
+    lib.marlnav_obs_size.argtypes = [i32, i32]
     got = lib.marlnav_abi_version()
     if got != ABI_VERSION:
         raise MarlnavError(f"libmarlnav_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild")

@@ -178,6 +178,7 @@ class Env(object):
             if init.get('noisy_ags'):
                 raise NotImplementedError("noisy_ags=True is hard-coded off in the reference "
                                           "(utils.py:25) and not implemented here")
+            self._tmpl_nonneg = not bool(torch.signbit(agents).any())
             self._tmpl_states = agents.to(dev).contiguous()
             self._tmpl_obstacles = None
             self._tmpl_target = torch.tensor([init['tar_pos_x'], init['tar_pos_y']], device=dev)
@@ -195,6 +196,7 @@ class Env(object):
             self._tmpl_target = torch.tensor(init['mock_target'], dtype=torch.float32,
                                              device=dev).reshape(B, 2).contiguous()
             self._per_env_template = True
+            self._tmpl_nonneg = False
         else:
             raise ValueError(f"unknown init_method {method!r}")
 
@@ -208,6 +210,7 @@ class Env(object):
         rs.obstacles_env_stride = self.num_obstacles * 2 if per_env else 0
         rs.target_env_stride = 2 if per_env else 0
         rs.alias_first_step = 1 if alias else 0
+        rs.flags = 1 if (not per_env and self._tmpl_nonneg) else 0      # MARLNAV_RESET_TMPL_NONNEG
         rs.seed, rs.step_counter, rs.env_id_offset = self._seed, self._reset_counter, self._env_id_offset
         return rs
 
@@ -292,6 +295,20 @@ class Env(object):
         trunc = buf[n_obs + n_rew + n_flag:n_obs + n_rew + n_flag + B]
         return obs, rew, term, trunc
 
+    def _step_call_cache(self):
+        """ctypes argument objects that never change between steps (state tensors are updated in
+        place, so their pointers are stable): built once, the per-step host cost is what bounds
+        small batches."""
+        c = self.__dict__.get('_call_cache')
+        if c is None:
+            rs = self._reset_spec(alias=False)
+            c = dict(rs=rs, rs_ref=ctypes.byref(rs), p_ref=ctypes.byref(self._c_params),
+                     fixed=(self._ptr(self.states), self._ptr(self.obstacles), self._ptr(self.target),
+                            self._ptr(self._step_num), self._ptr(self._terminates_u8)),
+                     stats=self._ptr(self._stats), fn=self._lib.marlnav_step_f32)
+            self._call_cache = c
+        return c
+
     def step_fused(self, actions, out=None):
         """One fused step.  Returns ``(obs (B,A,S), rewards (B), terminated (B) bool,
         truncated (B) bool)``; ``out`` may supply preallocated (obs, rewards,
@@ -304,18 +321,22 @@ class Env(object):
         with torch.cuda.device(self.device):
             obs, rew, term, trunc = out if out is not None else self._alloc_outputs()
             self._reset_counter += 1
-            rs = self._reset_spec(alias=self._alias_pending)
-            _lib.check(self._lib.marlnav_step_f32(
-                ctypes.byref(self._c_params), ctypes.byref(rs),
-                self._ptr(self.states), self._ptr(self.obstacles), self._ptr(self.target),
-                self._ptr(self._step_num), self._ptr(self._terminates_u8), self._ptr(actions),
-                self._ptr(obs), self._ptr(rew), self._ptr(term), self._ptr(trunc),
-                self._ptr(self._stats), ctypes.byref(self._io) if self._io is not None else None,
-                self._stream()), "marlnav_step_f32")
+            c = self._step_call_cache()
+            rs = c['rs']
+            rs.step_counter = self._reset_counter
+            if self._alias_pending:
+                rs.alias_first_step = 1
+            rc = c['fn'](c['p_ref'], c['rs_ref'], *c['fixed'], actions.data_ptr(),
+                         obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), c['stats'],
+                         ctypes.byref(self._io) if self._io is not None else None,
+                         torch.cuda.current_stream(self.device).cuda_stream)
+            if rc:
+                _lib.check(rc, "marlnav_step_f32")
             if self._alias_pending:
                 # the reference's template froze at "state after the first move" (B-6)
                 self._tmpl_states = self.states.clone()
                 self._alias_pending = False
+                self.__dict__.pop('_call_cache', None)      # template pointer changed
         return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
 
     def step(self, actions):

@@ -66,7 +66,7 @@ typedef struct {
     const float* tmpl_target;     /* (2) if stride 0, else (B,2) */
     int64_t states_env_stride, obstacles_env_stride, target_env_stride; /* in floats */
     int32_t alias_first_step;     /* MockInitializer aliasing quirk, SURVEY Appendix B-6 */
-    int32_t _pad;
+    int32_t flags;
     uint64_t seed, step_counter, env_id_offset;
 } mo_reset;
 

@@ -64,7 +64,7 @@ class MoReset(ctypes.Structure):
                 ("tmpl_target", ctypes.c_void_p),
                 ("states_env_stride", ctypes.c_int64), ("obstacles_env_stride", ctypes.c_int64),
                 ("target_env_stride", ctypes.c_int64),
-                ("alias_first_step", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("alias_first_step", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
                 ("env_id_offset", ctypes.c_uint64)]
 
