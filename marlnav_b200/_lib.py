@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmarlnav_b200.so")
+# MARLNAV_B200_LIB may point at another build of the same ABI (A/B measurements only)
+LIB_PATH = os.environ.get("MARLNAV_B200_LIB") or os.path.join(_HERE, "libmarlnav_b200.so")
 
 ABI_VERSION = 1
 
