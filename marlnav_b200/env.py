@@ -375,17 +375,22 @@ class HostStepper:
         self.h2d_bytes = self.actions_host.numel() * 4
         self.d2h_bytes = self.obs_host.numel() * 4 + B * 4 + 2 * B
 
-    def step(self, sync=True):
-        """Consumes ``self.actions_host``; fills the ``*_host`` outputs."""
+    def step(self, actions=None, sync=True):
+        """Consumes ``actions`` (a pinned CPU float32 tensor of shape (B,A,2); default
+        ``self.actions_host``) and fills the ``*_host`` outputs."""
         env = self.env
         p = Env._ptr
+        src = self.actions_host if actions is None else actions
+        if src.device.type != 'cpu' or src.dtype != torch.float32 or not src.is_contiguous() \
+                or src.numel() != self.actions_host.numel():
+            raise _lib.MarlnavError("HostStepper.step needs a contiguous float32 CPU tensor of shape (B,A,2)")
         with torch.cuda.device(env.device):
             env._reset_counter += 1
             rs = env._reset_spec(alias=env._alias_pending)
             _lib.check(env._lib.marlnav_step_host_f32(
                 ctypes.byref(env._c_params), ctypes.byref(rs),
                 p(env.states), p(env.obstacles), p(env.target), p(env._step_num), p(env._terminates_u8),
-                p(self.actions_host), p(self.actions_dev), p(self.obs_dev), p(self.rewards_dev),
+                p(src), p(self.actions_dev), p(self.obs_dev), p(self.rewards_dev),
                 p(self.terminated_dev), p(self.truncated_dev),
                 p(self.obs_host), p(self.rewards_host), p(self.terminated_host), p(self.truncated_host),
                 p(env._stats), ctypes.byref(env._io) if env._io is not None else None,
@@ -393,5 +398,6 @@ class HostStepper:
             if env._alias_pending:
                 env._tmpl_states = env.states.clone()
                 env._alias_pending = False
+                env.__dict__.pop('_call_cache', None)
             if sync:
                 torch.cuda.current_stream(env.device).synchronize()
