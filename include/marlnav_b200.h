@@ -158,6 +158,36 @@ int marlnav_step_host_f32(const marlnav_env_params* params, const marlnav_reset_
 int marlnav_step_launch_info(const marlnav_env_params* params,
                              int* grid, int* block, int* smem_bytes, int* envs_per_cta);
 
+/* ---- caller-side rows that come next after the step ---- */
+
+/* Actor.forward + dist.sample() + dist.log_prob(actions), marlnav/models.py:27-36,113-115, for
+ * N = B*A rows of normalised observations (obs_size S, hidden H; the reference has S=12, H=50):
+ *   h = fc1(x)  (no activation, models.py:29);  mu = tanh(fc_mu(h));  var = softplus(fc_std(h))
+ *   dist = MultivariateNormal(mu, covariance_matrix=diag(var))        (models.py:32-34)
+ *   actions = mu + sqrt(var)*eps;  log_probs = dist.log_prob(actions)
+ * Weights are torch.nn.Linear layouts: w1 (H,S), b1 (H), w_mu/w_std (2,H), b_mu/b_std (2).
+ * eps (N,2): standard-normal draws to use (parity tests) or NULL -> Philox4x32-10 + Box-Muller
+ * addressed by (seed; row, counter).  mu_out/var_out (N,2) may be NULL. */
+int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H,
+                             const float* w1, const float* b1, const float* w_mu, const float* b_mu,
+                             const float* w_std, const float* b_std,
+                             const float* eps, uint64_t seed, uint64_t counter,
+                             float* actions, float* log_probs, float* mu_out, float* var_out, void* stream);
+
+/* Critic.forward, marlnav/models.py:39-56: values (B) = fc2(relu(fc1(x))) for x = the env's
+ * flattened normalised observations (K = A*S inputs, hidden H <= 64; reference: 36 -> 50 -> 1).
+ * w1 (H,K), b1 (H), w2 (1,H), b2 (1) in torch.nn.Linear layout. */
+int marlnav_critic_value_f32(const float* obs, long long B, int K, int H,
+                             const float* w1, const float* b1, const float* w2, const float* b2,
+                             float* values, void* stream);
+
+/* The backward scan of MAPPO._process_rewards, marlnav/models.py:131-139, in float64 like the
+ * reference: out[t] = done[t] ? 0 : rewards[t] + gamma * out[t+1], t = T-1..0, (T,B) row-major. */
+int marlnav_discounted_returns_f64(const float* rewards, const uint8_t* done, double gamma,
+                                   int T, long long B, double* out, void* stream);
+
+const char* marlnav_rollout_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

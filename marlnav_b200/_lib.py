@@ -15,7 +15,9 @@ ABI_VERSION = 1
 # every symbol include/marlnav_b200.h declares
 EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",
            "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
-           "marlnav_step_launch_info")
+           "marlnav_step_launch_info", "marlnav_actor_sample_f32", "marlnav_critic_value_f32",
+           "marlnav_discounted_returns_f64",
+           "marlnav_rollout_last_error")
 
 
 class EnvParams(ctypes.Structure):
@@ -67,8 +69,9 @@ def load():
             "(nvcc, sm_100a). marlnav_b200 has no CPU or PyTorch fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     lib.marlnav_last_error.restype = ctypes.c_char_p
+    lib.marlnav_rollout_last_error.restype = ctypes.c_char_p
     for name in EXPORTS:
-        if name != "marlnav_last_error":
+        if name not in ("marlnav_last_error", "marlnav_rollout_last_error"):
             getattr(lib, name).restype = ctypes.c_int
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     lib.marlnav_step_f32.argtypes = [vp] * 15
@@ -76,6 +79,10 @@ def load():
     lib.marlnav_init_f32.argtypes = [vp] * 8
     lib.marlnav_step_host_f32.argtypes = [vp] * 20
     lib.marlnav_obs_size.argtypes = [i32, i32]
+    i64, u64, f64 = ctypes.c_longlong, ctypes.c_uint64, ctypes.c_double
+    lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64] + [vp] * 5
+    lib.marlnav_discounted_returns_f64.argtypes = [vp, vp, f64, i32, i64, vp, vp]
+    lib.marlnav_critic_value_f32.argtypes = [vp, i64, i32, i32] + [vp] * 6
     got = lib.marlnav_abi_version()
     if got != ABI_VERSION:
         raise MarlnavError(f"libmarlnav_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild")

@@ -12,7 +12,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "marlnav_kernels.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "marlnav_math.cuh"),
+SRC2 = os.path.join(_HERE, "csrc", "marlnav_rollout.cu")
+DEPS = [SRC, SRC2, os.path.join(_HERE, "csrc", "marlnav_math.cuh"),
         os.path.join(os.path.dirname(_HERE), "include", "marlnav_b200.h")]
 LIB = os.path.join(_HERE, "libmarlnav_b200.so")
 
@@ -33,7 +34,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
         return LIB
     extra = os.environ.get("MARLNAV_NVCC_EXTRA", "").split()      # e.g. -DMN_W1_WARPS=5 for A/B builds
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC, SRC2]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -1,0 +1,174 @@
+"""Caller-side pieces around the fused step.
+
+* ``FusedActor``          -- the reference's ``Actor.forward`` + ``dist.sample()`` +
+                             ``dist.log_prob()`` (/root/reference/marlnav/models.py:27-36,113-115)
+                             as one kernel launch (``marlnav_actor_sample_f32``).
+* ``discounted_returns``  -- the backward scan of ``MAPPO._process_rewards``
+                             (models.py:131-139) as one kernel (``marlnav_discounted_returns_f64``),
+                             optionally followed by its std/mean normalisation (models.py:141-145).
+* ``collect_rollout``     -- ``MAPPO.get_data`` (models.py:106-129) with device-resident (T, ...)
+                             buffers instead of a Python list of lists: per step one actor launch and
+                             one fused environment step (normaliser and action scaler folded in).
+
+The reference's learner itself (PPO losses, Adam) is out of scope and stays stock PyTorch; these
+functions hand it tensors in the layouts it already uses.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _rollout_check(rc, what):
+    if rc != 0:
+        msg = _lib.load().marlnav_rollout_last_error().decode(errors="replace")
+        raise _lib.MarlnavError(f"{what} failed (code {rc}): {msg}")
+
+
+class FusedActor:
+    """Inference-side twin of the reference ``Actor`` (models.py:14-36): takes its weights
+    (``fc1``, ``fc_mu``, ``fc_std``) and samples actions + log-probs in one launch."""
+
+    def __init__(self, actor, device='cuda', seed=None):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.MarlnavError("FusedActor needs a CUDA device (no CPU fallback)")
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self.counter = 0
+        self.refresh(actor)
+
+    def refresh(self, actor):
+        """(Re-)read the weights, e.g. after optimiser steps.  ``actor`` is the reference's
+        ``Actor`` module or its ``state_dict()``."""
+        sd = actor if isinstance(actor, dict) else actor.state_dict()
+        g = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.w1, self.b1 = g('fc1.weight'), g('fc1.bias')
+        self.w_mu, self.b_mu = g('fc_mu.weight'), g('fc_mu.bias')
+        self.w_std, self.b_std = g('fc_std.weight'), g('fc_std.bias')
+        self.hidden, self.obs_size = self.w1.shape
+        if self.w_mu.shape != (2, self.hidden) or self.w_std.shape != (2, self.hidden):
+            raise _lib.MarlnavError("unexpected Actor head shapes (need 2 outputs)")
+
+    def act(self, obs, eps=None, want_moments=False, out=None):
+        """``obs``: normalised observations (..., obs_size) on the device (e.g. the fused (B,A,S)
+        buffer).  Returns ``(actions (N,2), log_probs (N,))`` with N = prod(leading dims), exactly
+        what models.py:113-115 produces; ``eps`` (N,2) injects the normal draws (tests); ``out`` =
+        preallocated contiguous ``(actions, log_probs)`` tensors to write into."""
+        x = obs.reshape(-1, self.obs_size)
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        with torch.cuda.device(self.device):
+            if out is not None:
+                actions, log_probs = out
+            else:
+                actions = torch.empty(n, 2, device=self.device)
+                log_probs = torch.empty(n, device=self.device)
+            mu = torch.empty(n, 2, device=self.device) if want_moments else None
+            var = torch.empty(n, 2, device=self.device) if want_moments else None
+            if eps is not None:
+                eps = eps.to(device=self.device, dtype=torch.float32).contiguous()
+            self.counter += 1
+            p = lambda t: t.data_ptr() if t is not None else None
+            _rollout_check(self._lib.marlnav_actor_sample_f32(
+                p(x), n, self.obs_size, self.hidden, p(self.w1), p(self.b1), p(self.w_mu), p(self.b_mu),
+                p(self.w_std), p(self.b_std), p(eps), self.seed, self.counter, p(actions), p(log_probs),
+                p(mu), p(var), torch.cuda.current_stream(self.device).cuda_stream), "marlnav_actor_sample_f32")
+        return (actions, log_probs, mu, var) if want_moments else (actions, log_probs)
+
+
+class FusedCritic:
+    """Inference-side twin of the reference ``Critic`` (models.py:39-56): one launch per batch."""
+
+    def __init__(self, critic, device='cuda'):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.MarlnavError("FusedCritic needs a CUDA device (no CPU fallback)")
+        self.refresh(critic)
+
+    def refresh(self, critic):
+        sd = critic if isinstance(critic, dict) else critic.state_dict()
+        g = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.w1, self.b1, self.w2, self.b2 = g('fc1.weight'), g('fc1.bias'), g('fc2.weight'), g('fc2.bias')
+        self.hidden, self.inputs = self.w1.shape
+
+    def __call__(self, obs, out=None):
+        """``obs``: (B, ...) normalised observations with prod(...) == inputs.  Returns (B,1)."""
+        x = obs.reshape(obs.shape[0], -1)
+        if x.shape[1] != self.inputs:
+            raise _lib.MarlnavError(f"critic expects {self.inputs} inputs per env, got {x.shape[1]}")
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            v = out if out is not None else torch.empty(x.shape[0], 1, device=self.device)
+            _rollout_check(self._lib.marlnav_critic_value_f32(
+                x.data_ptr(), x.shape[0], self.inputs, self.hidden, self.w1.data_ptr(), self.b1.data_ptr(),
+                self.w2.data_ptr(), self.b2.data_ptr(), v.data_ptr(),
+                torch.cuda.current_stream(self.device).cuda_stream), "marlnav_critic_value_f32")
+        return v
+
+
+def discounted_returns(rewards, done, gamma, normalize=False):
+    """models.py:131-139: ``curr = where(done, 0, rew + gamma*curr)`` backwards over the buffer, in
+    float64 like the reference.  ``rewards`` (T,B) float32, ``done`` (T,B) bool/uint8, on the device.
+    ``normalize=True`` also applies models.py:141-145: ``(x - mean) / (std + 1e-12)`` over the buffer."""
+    lib = _lib.load()
+    if rewards.device.type != 'cuda':
+        raise _lib.MarlnavError("discounted_returns needs CUDA tensors (no CPU fallback)")
+    T, B = rewards.shape
+    rewards = rewards.to(torch.float32).contiguous()
+    done_u8 = (done.view(torch.uint8) if done.dtype == torch.bool else done.to(torch.uint8)).contiguous()
+    with torch.cuda.device(rewards.device):
+        out = torch.empty(T, B, dtype=torch.float64, device=rewards.device)
+        _rollout_check(lib.marlnav_discounted_returns_f64(
+            rewards.data_ptr(), done_u8.data_ptr(), float(gamma), int(T), int(B), out.data_ptr(),
+            torch.cuda.current_stream(rewards.device).cuda_stream), "marlnav_discounted_returns_f64")
+        if normalize:
+            std, mean = torch.std_mean(out.reshape(-1))
+            out = (out - mean) / (std + 1e-12)
+    return out
+
+
+@torch.no_grad()
+def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None, scaler_params=None):
+    """``MAPPO.get_data`` (models.py:106-129) on device-resident buffers.
+
+    ``env``: a ``marlnav_b200.Env``; ``actor``: a ``FusedActor``; ``critic``: optional ``FusedCritic``
+    or torch module taking (B, A*S) normalised observations (the reference's ``Critic``).  The env must have its
+    normaliser / action scaler fused in (``env.fuse_io``); pass the reference's ``normalizer`` /
+    ``scaler`` param dicts here to do that.  Returns a dict of tensors with a leading time axis:
+    ``obs (T,B,A,S)``, ``actions (T,B*A,2)``, ``log_probs (T,B*A)``, ``rewards (T,B)``, ``done (T,B)``
+    and ``values (T,B,1)`` when a critic is given."""
+    if normalizer_params is not None or scaler_params is not None:
+        env.fuse_io(normalizer_params, scaler_params)
+    if env._io is None or not env._io.obs_mean or not env._io.act_scale:
+        raise _lib.MarlnavError("collect_rollout needs env.fuse_io(normalizer, scaler) first")
+    B, A, S, T = env.num_parallel, env.num_agents, env.obs_size, int(buffer_len)
+    dev = env.device
+    mean, scale = env._io_tensors[0], env._io_tensors[1]
+    # every kernel writes straight into its slice of the buffers: two launches per step
+    obs_all = torch.empty(T + 1, B, A, S, device=dev)
+    term = torch.empty(T, B, dtype=torch.uint8, device=dev)
+    trunc = torch.empty(T, B, dtype=torch.uint8, device=dev)
+    buf = dict(actions=torch.empty(T, B * A, 2, device=dev), log_probs=torch.empty(T, B * A, device=dev),
+               rewards=torch.empty(T, B, device=dev))
+    if critic is not None:
+        buf['values'] = torch.empty(T, B, 1, device=dev)
+    torch.div(env.observations_fused() - mean, scale, out=obs_all[0])          # models.py:110
+    for t in range(T):
+        obs = obs_all[t]
+        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
+        if critic is not None:
+            if isinstance(critic, FusedCritic):
+                critic(obs.view(B, A * S), out=buf['values'][t])                # models.py:120
+            else:
+                buf['values'][t].copy_(critic(obs.view(B, A * S)))
+        # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
+        env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
+    buf['obs'] = obs_all[:T]
+    buf['last_obs'] = obs_all[T]
+    buf['done'] = torch.logical_or(term.view(torch.bool), trunc.view(torch.bool))   # models.py:119
+    return buf

@@ -450,3 +450,32 @@ class TorchPortEnv:
             blend(self.target, nt)
         self.step_num = blend(self.step_num, t.zeros(self.B))
         return self.observations(), rew, terminated, truncated
+
+
+# ------------------------------------------------ caller-side rows
+
+def actor_reference(obs, weights, eps):
+    """Actor.forward + sample + log_prob exactly as the reference composes them with torch
+    (models.py:27-36,113-115), with the normal draws injected: sample = mu + sqrt(var) * eps,
+    which is what MultivariateNormal(mu, diag(var)).rsample does with its Cholesky factor."""
+    import torch
+    from torch.distributions import MultivariateNormal
+    x = obs.reshape(-1, obs.shape[-1])
+    h = torch.nn.functional.linear(x, weights['fc1.weight'], weights['fc1.bias'])
+    mu = torch.tanh(torch.nn.functional.linear(h, weights['fc_mu.weight'], weights['fc_mu.bias']))
+    var = torch.nn.functional.softplus(torch.nn.functional.linear(h, weights['fc_std.weight'], weights['fc_std.bias']))
+    dist = MultivariateNormal(mu, torch.vmap(torch.diag)(var))
+    actions = mu + torch.sqrt(var) * eps
+    return actions, dist.log_prob(actions), mu, var
+
+
+def discounted_returns_reference(rewards, done, gamma):
+    """models.py:131-139 restated with the same torch ops (float64 accumulator, torch.where)."""
+    import torch
+    T, B = rewards.shape
+    curr = torch.zeros(B, dtype=float)
+    out = torch.empty(T, B, dtype=torch.float64)
+    for i in range(T - 1, -1, -1):
+        curr = torch.where(done[i], 0., rewards[i] + gamma * curr)
+        out[i] = curr
+    return out

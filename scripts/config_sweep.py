@@ -106,6 +106,29 @@ def rollout_line(B=1024, A=3, O=3, steps=1000):
     res["cuda_graph_env_steps_per_sec"] = B * reps * unroll / (time.perf_counter() - t0)
     res["note"] = ("graph = 50 {actor -> fused step} iterations; replays reuse the captured Philox step "
                    "counters, fine for throughput, not for training")
+    # fused actor kernel + device-resident rollout buffers (marlnav_b200.rollout)
+    fa = mb.FusedActor(actor.state_dict().__class__(
+        {'fc1.weight': actor.fc1.weight, 'fc1.bias': actor.fc1.bias, 'fc_mu.weight': actor.mu.weight,
+         'fc_mu.bias': actor.mu.bias, 'fc_std.weight': actor.std.weight, 'fc_std.bias': actor.std.bias}), seed=1)
+    critic = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(A * env.obs_size, 50), torch.nn.ReLU(),
+                                 torch.nn.Linear(50, 1)).cuda()
+    fcrit = mb.FusedCritic({'fc1.weight': critic[1].weight, 'fc1.bias': critic[1].bias,
+                            'fc2.weight': critic[3].weight, 'fc2.bias': critic[3].bias})
+    for name, cr in (("fused_actor_rollout_env_steps_per_sec", None), ("fused_actor_plus_torch_critic_env_steps_per_sec", critic),
+                     ("fused_actor_plus_fused_critic_env_steps_per_sec", fcrit)):
+        mb.collect_rollout(env, fa, 50, critic=cr)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        buf = mb.collect_rollout(env, fa, steps, critic=cr)
+        torch.cuda.synchronize(); res[name] = B * steps / (time.perf_counter() - t0)
+    for rep in range(2):                                   # second pass = warm
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ret = mb.discounted_returns(buf['rewards'], buf['done'], 0.9, normalize=True)
+        torch.cuda.synchronize(); res["discounted_returns_ms_T1000"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        curr = torch.zeros(B, dtype=float, device='cuda')
+        for i in range(steps - 1, -1, -1):                 # the reference's loop, models.py:135-139
+            curr = torch.where(buf['done'][i], 0., buf['rewards'][i] + 0.9 * curr)
+        torch.cuda.synchronize(); res["reference_return_loop_ms_T1000"] = 1e3 * (time.perf_counter() - t0)
     return {"config": f"rollout {B}x{A}x{O} with actor in the loop (BASELINE configs[1])", **res}
 
 

@@ -1,0 +1,117 @@
+"""GPU: the caller-side kernels against torch restatements of
+the reference's learner code (oracle.actor_reference / oracle.discounted_returns_reference)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _actor_weights(S=12, H=50, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    w = {'fc1.weight': torch.empty(H, S), 'fc_mu.weight': torch.empty(2, H), 'fc_std.weight': torch.empty(2, H)}
+    for v in w.values():
+        torch.nn.init.orthogonal_(v, generator=g)          # models.py:20-24
+    w.update({'fc1.bias': torch.rand(H, generator=g) * 0.2 - 0.1, 'fc_mu.bias': torch.rand(2, generator=g) - 0.5,
+              'fc_std.bias': torch.rand(2, generator=g) - 0.5})
+    return w
+
+
+@pytest.mark.parametrize("S,H,N", [(12, 50, 3072), (48, 50, 1000), (8, 7, 33)])
+def test_fused_actor_matches_torch(oracle, S, H, N):
+    import marlnav_b200 as mb
+    w = _actor_weights(S, H)
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(N, S, generator=g) * 2 - 1
+    eps = torch.randn(N, 2, generator=g)
+    fa = mb.FusedActor(w, seed=5)
+    act, lp, mu, var = fa.act(obs.cuda(), eps=eps, want_moments=True)
+    r_act, r_lp, r_mu, r_var = oracle.actor_reference(obs, w, eps)
+    # float32 dot products in a different association than torch's GEMM: 1e-5 relative
+    np.testing.assert_allclose(mu.cpu().numpy(), r_mu.numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), r_var.numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(act.cpu().numpy(), r_act.numpy(), rtol=1e-5, atol=5e-6)
+    np.testing.assert_allclose(lp.cpu().numpy(), r_lp.numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_fused_actor_sampling_is_standard_normal_and_addressed():
+    import marlnav_b200 as mb
+    w = _actor_weights()
+    obs = torch.zeros(1 << 18, 12)
+    fa = mb.FusedActor(w, seed=9)
+    act, lp, mu, var = fa.act(obs.cuda(), want_moments=True)
+    z = ((act - mu) / var.sqrt()).cpu().double()
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs((z[:, 0] * z[:, 1]).mean()) < 0.01                      # independent components
+    assert abs((z ** 4).mean() - 3) < 0.1                              # Gaussian kurtosis
+    fb = mb.FusedActor(w, seed=9)
+    act2, _ = fb.act(obs.cuda())
+    assert torch.equal(act, act2)                                      # (seed, counter, row) addressed
+    act3, _ = fb.act(obs.cuda())
+    assert not torch.equal(act2, act3)                                 # next call, next counter
+    want_lp = -0.5 * (z ** 2).sum(1) - 0.5 * var.cpu().double().log().sum(1) - math.log(2 * math.pi)
+    np.testing.assert_allclose(lp.cpu().double().numpy(), want_lp.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("T,B", [(1000, 257), (37, 4096)])
+def test_discounted_returns_bit_exact(oracle, T, B):
+    """Same float64 operations in the same order as models.py:131-139 -> identical bits."""
+    import marlnav_b200 as mb
+    g = torch.Generator().manual_seed(3)
+    rew = (torch.rand(T, B, generator=g) * 700 - 350)
+    done = torch.rand(T, B, generator=g) < 0.02
+    got = mb.discounted_returns(rew.cuda(), done.cuda(), 0.9).cpu()
+    want = oracle.discounted_returns_reference(rew, done, 0.9)
+    assert torch.equal(got, want)
+    norm = mb.discounted_returns(rew.cuda(), done.cuda(), 0.9, normalize=True).cpu()
+    std, mean = torch.std_mean(want.reshape(-1))
+    np.testing.assert_allclose(norm.numpy(), ((want - mean) / (std + 1e-12)).numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_collect_rollout_matches_stepwise_loop(oracle):
+    """collect_rollout == calling FusedActor.act / Env.step_fused by hand with the same seeds, and
+    its buffers have the layouts MAPPO.get_data stores (models.py:121)."""
+    import marlnav_b200 as mb
+    B, A, O, T = 512, 3, 3, 40
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm, scal = dict(min_obs=lo, max_obs=hi), dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    w = _actor_weights()
+    envs = []
+    for _ in range(2):
+        p = mb.default_env_params(B, A, O, sampling_style='policy'); p['seed'] = 4
+        envs.append(mb.Env(p))
+    critic = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(A * 12, 50), torch.nn.ReLU(), torch.nn.Linear(50, 1)).cuda()
+    buf = mb.collect_rollout(envs[0], mb.FusedActor(w, seed=11), T, critic=critic, normalizer_params=norm, scaler_params=scal)
+    assert buf['obs'].shape == (T, B, A, 12) and buf['actions'].shape == (T, B * A, 2)
+    assert buf['log_probs'].shape == (T, B * A) and buf['rewards'].shape == (T, B) and buf['values'].shape == (T, B, 1)
+    assert buf['done'].dtype == torch.bool and bool(buf['done'].any())
+    env, fa = envs[1], mb.FusedActor(w, seed=11)
+    env.fuse_io(norm, scal)
+    obs = (env.observations_fused() - env._io_tensors[0]) / env._io_tensors[1]
+    for t in range(T):
+        assert torch.equal(buf['obs'][t], obs)
+        act, lp = fa.act(obs)
+        assert torch.equal(buf['actions'][t], act) and torch.equal(buf['log_probs'][t], lp)
+        obs, rew, term, trunc = env.step_fused(act.view(B, A, 2))
+        assert torch.equal(buf['rewards'][t], rew) and torch.equal(buf['done'][t], term | trunc)
+    ret = mb.discounted_returns(buf['rewards'], buf['done'], 0.9, normalize=True)
+    assert ret.shape == (T, B) and ret.dtype == torch.float64 and bool(torch.isfinite(ret).all())
+
+
+@pytest.mark.parametrize("K,H,B", [(36, 50, 1024), (384, 50, 300), (16, 7, 5)])
+def test_fused_critic_matches_torch(K, H, B):
+    """Critic.forward (models.py:39-56) as one kernel vs the torch module."""
+    import marlnav_b200 as mb
+    g = torch.Generator().manual_seed(2)
+    fc1, fc2 = torch.nn.Linear(K, H), torch.nn.Linear(H, 1)
+    torch.nn.init.orthogonal_(fc1.weight, generator=g); torch.nn.init.orthogonal_(fc2.weight, generator=g)
+    sd = {'fc1.weight': fc1.weight, 'fc1.bias': fc1.bias, 'fc2.weight': fc2.weight, 'fc2.bias': fc2.bias}
+    x = torch.rand(B, K, generator=g) * 2 - 1
+    want = fc2(torch.relu(fc1(x))).detach()
+    got = mb.FusedCritic(sd)(x.cuda()).cpu()
+    assert got.shape == (B, 1)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=5e-6)
