@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MARLNAV_ABI_VERSION 1
+#define MARLNAV_ABI_VERSION 2
 #define MARLNAV_MAX_AGENTS 26     /* torch.cdist's direct formula holds up to 25 columns */
 #define MARLNAV_MAX_OBSTACLES 64
 
@@ -88,6 +88,10 @@ typedef struct marlnav_reset_spec {
     uint64_t seed;
     uint64_t step_counter;     /* 0 at construction, k for the k-th step() call */
     uint64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */
+    const uint64_t* step_counter_dev;  /* if non-NULL the kernels read the step counter from this DEVICE
+                                        * word instead of `step_counter`, so a captured CUDA graph draws
+                                        * fresh reset positions on every replay (bump it with
+                                        * marlnav_counter_add before each step) */
 } marlnav_reset_spec;
 
 /* Optional fused caller-side transforms:
@@ -107,6 +111,10 @@ const char* marlnav_last_error(void);
 int         marlnav_obs_size(int num_agents, int num_obstacles);
 /* Number of CUDA devices visible (0 when there is none / no driver). */
 int         marlnav_device_count(void);
+
+/* *counter += inc on the stream (one-thread kernel; graph-capturable).  Used to advance the
+ * device-resident step counters of marlnav_reset_spec / marlnav_actor_sample_f32. */
+int marlnav_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /* Env.__init__'s first `self._init_sampler()` + counters (environment.py:26-40):
  * fills states/obstacles/target from `reset` (step_counter is used as given,
@@ -167,11 +175,12 @@ int marlnav_step_launch_info(const marlnav_env_params* params,
  *   actions = mu + sqrt(var)*eps;  log_probs = dist.log_prob(actions)
  * Weights are torch.nn.Linear layouts: w1 (H,S), b1 (H), w_mu/w_std (2,H), b_mu/b_std (2).
  * eps (N,2): standard-normal draws to use (parity tests) or NULL -> Philox4x32-10 + Box-Muller
- * addressed by (seed; row, counter).  mu_out/var_out (N,2) may be NULL. */
+ * addressed by (seed; row, counter); counter_dev, if non-NULL, overrides `counter` with a DEVICE
+ * word (CUDA-graph replays).  mu_out/var_out (N,2) may be NULL. */
 int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H,
                              const float* w1, const float* b1, const float* w_mu, const float* b_mu,
                              const float* w_std, const float* b_std,
-                             const float* eps, uint64_t seed, uint64_t counter,
+                             const float* eps, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
                              float* actions, float* log_probs, float* mu_out, float* var_out, void* stream);
 
 /* Critic.forward, marlnav/models.py:39-56: values (B) = fc2(relu(fc1(x))) for x = the env's

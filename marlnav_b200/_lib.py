@@ -10,11 +10,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MARLNAV_B200_LIB may point at another build of the same ABI (A/B measurements only)
 LIB_PATH = os.environ.get("MARLNAV_B200_LIB") or os.path.join(_HERE, "libmarlnav_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/marlnav_b200.h declares
 EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",
-           "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
+           "marlnav_counter_add", "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
            "marlnav_step_launch_info", "marlnav_actor_sample_f32", "marlnav_critic_value_f32",
            "marlnav_discounted_returns_f64",
            "marlnav_rollout_last_error")
@@ -42,7 +42,7 @@ class ResetSpec(ctypes.Structure):
                 ("target_env_stride", ctypes.c_int64),
                 ("alias_first_step", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
-                ("env_id_offset", ctypes.c_uint64)]
+                ("env_id_offset", ctypes.c_uint64), ("step_counter_dev", ctypes.c_void_p)]
 
 
 class IoTransform(ctypes.Structure):
@@ -80,7 +80,8 @@ def load():
     lib.marlnav_step_host_f32.argtypes = [vp] * 20
     lib.marlnav_obs_size.argtypes = [i32, i32]
     i64, u64, f64 = ctypes.c_longlong, ctypes.c_uint64, ctypes.c_double
-    lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64] + [vp] * 5
+    lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64] + [vp] * 6
+    lib.marlnav_counter_add.argtypes = [vp, u64, vp]
     lib.marlnav_discounted_returns_f64.argtypes = [vp, vp, f64, i32, i64, vp, vp]
     lib.marlnav_critic_value_f32.argtypes = [vp, i64, i32, i32] + [vp] * 6
     got = lib.marlnav_abi_version()

@@ -43,6 +43,7 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
                     const float* __restrict__ w_mu, const float* __restrict__ b_mu,
                     const float* __restrict__ w_std, const float* __restrict__ b_std,
                     const float* __restrict__ eps, uint64_t seed, uint64_t counter,
+                    const unsigned long long* __restrict__ counter_dev,
                     float* __restrict__ actions, float* __restrict__ log_probs,
                     float* __restrict__ mu_out, float* __restrict__ var_out) {
     extern __shared__ float sm[];
@@ -76,6 +77,7 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
     float e0, e1;
     if (eps) { e0 = eps[row * 2]; e1 = eps[row * 2 + 1]; }
     else {
+        if (counter_dev) counter = __ldg(counter_dev);
         const uint4 r = philox4x32_10((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)counter,
                                       0x41435452u /* 'ACTR' */, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u1 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-08f;      // (0, 1]
@@ -165,8 +167,8 @@ const char* marlnav_rollout_last_error(void) { return g_err2; }
 
 int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H, const float* w1, const float* b1,
                              const float* w_mu, const float* b_mu, const float* w_std, const float* b_std,
-                             const float* eps, uint64_t seed, uint64_t counter, float* actions,
-                             float* log_probs, float* mu_out, float* var_out, void* stream) {
+                             const float* eps, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                             float* actions, float* log_probs, float* mu_out, float* var_out, void* stream) {
     if (!obs || !w1 || !b1 || !w_mu || !b_mu || !w_std || !b_std || !actions || !log_probs || N < 1) {
         snprintf(g_err2, sizeof g_err2, "marlnav_actor_sample_f32: NULL pointer or empty batch");
         return MARLNAV_ERR_BAD_ARG;
@@ -181,10 +183,12 @@ int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (S <= 16)
         mnr::actor_sample_kernel<16, 256><<<(unsigned)grid, threads, smem, st>>>(
-            obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter, actions, log_probs, mu_out, var_out);
+            obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter,
+            reinterpret_cast<const unsigned long long*>(counter_dev), actions, log_probs, mu_out, var_out);
     else
         mnr::actor_sample_kernel<64, 256><<<(unsigned)grid, threads, smem, st>>>(
-            obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter, actions, log_probs, mu_out, var_out);
+            obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter,
+            reinterpret_cast<const unsigned long long*>(counter_dev), actions, log_probs, mu_out, var_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err2, sizeof g_err2, "actor_sample launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

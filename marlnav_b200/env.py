@@ -118,6 +118,7 @@ class Env(object):
         self._seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self._env_id_offset = int(params.get('env_id_offset', 0))
         self._reset_counter = 0
+        self._counter_dev = None          # device-resident copy of the counter (use_device_counter)
 
         self._c_params = self._make_c_params()
         self._setup_reset_source(params['init'])
@@ -212,6 +213,7 @@ class Env(object):
         rs.alias_first_step = 1 if alias else 0
         rs.flags = 1 if (not per_env and self._tmpl_nonneg) else 0      # MARLNAV_RESET_TMPL_NONNEG
         rs.seed, rs.step_counter, rs.env_id_offset = self._seed, self._reset_counter, self._env_id_offset
+        rs.step_counter_dev = self._counter_dev.data_ptr() if self._counter_dev is not None else None
         return rs
 
     # ------------------------------------------------------------------ episode statistics
@@ -244,6 +246,17 @@ class Env(object):
 
     def sample_actions(self):
         return self._sampler()
+
+    def use_device_counter(self, enable=True):
+        """Keep the reset step counter in device memory (advanced by a one-thread kernel before
+        every step) instead of passing it from the host.  Results are identical; the point is that
+        a CUDA graph capturing ``step`` then draws fresh reset positions on every replay."""
+        if enable and self._counter_dev is None:
+            self._counter_dev = torch.full((1,), self._reset_counter, dtype=torch.int64, device=self.device)
+        elif not enable and self._counter_dev is not None:
+            self._reset_counter = int(self._counter_dev.item())
+            self._counter_dev = None
+        self.__dict__.pop('_call_cache', None)
 
     def fuse_io(self, normalizer_params=None, scaler_params=None):
         """Fold the caller-side ObsNormalizer (utils.py:519-532) and/or ActionScaler
@@ -324,6 +337,9 @@ class Env(object):
             c = self._step_call_cache()
             rs = c['rs']
             rs.step_counter = self._reset_counter
+            if self._counter_dev is not None:
+                self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1,
+                                              torch.cuda.current_stream(self.device).cuda_stream)
             if self._alias_pending:
                 rs.alias_first_step = 1
             rc = c['fn'](c['p_ref'], c['rs_ref'], *c['fixed'], actions.data_ptr(),
@@ -386,6 +402,8 @@ class HostStepper:
             raise _lib.MarlnavError("HostStepper.step needs a contiguous float32 CPU tensor of shape (B,A,2)")
         with torch.cuda.device(env.device):
             env._reset_counter += 1
+            if env._counter_dev is not None:
+                env._lib.marlnav_counter_add(env._counter_dev.data_ptr(), 1, env._stream())
             rs = env._reset_spec(alias=env._alias_pending)
             _lib.check(env._lib.marlnav_step_host_f32(
                 ctypes.byref(env._c_params), ctypes.byref(rs),

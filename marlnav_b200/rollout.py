@@ -37,6 +37,8 @@ class FusedActor:
             raise _lib.MarlnavError("FusedActor needs a CUDA device (no CPU fallback)")
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.counter = 0
+        self._counter_dev = None
+        self.w1 = None
         self.refresh(actor)
 
     def refresh(self, actor):
@@ -44,12 +46,26 @@ class FusedActor:
         ``Actor`` module or its ``state_dict()``."""
         sd = actor if isinstance(actor, dict) else actor.state_dict()
         g = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
-        self.w1, self.b1 = g('fc1.weight'), g('fc1.bias')
-        self.w_mu, self.b_mu = g('fc_mu.weight'), g('fc_mu.bias')
-        self.w_std, self.b_std = g('fc_std.weight'), g('fc_std.bias')
+        new = [g(k) for k in ('fc1.weight', 'fc1.bias', 'fc_mu.weight', 'fc_mu.bias', 'fc_std.weight', 'fc_std.bias')]
+        if self.w1 is not None and all(o.shape == n.shape for o, n in zip(self._weights(), new)):
+            for o, n in zip(self._weights(), new):       # in place: captured CUDA graphs keep pointing here
+                o.copy_(n)
+        else:
+            self.w1, self.b1, self.w_mu, self.b_mu, self.w_std, self.b_std = new
         self.hidden, self.obs_size = self.w1.shape
         if self.w_mu.shape != (2, self.hidden) or self.w_std.shape != (2, self.hidden):
             raise _lib.MarlnavError("unexpected Actor head shapes (need 2 outputs)")
+
+    def _weights(self):
+        return [self.w1, self.b1, self.w_mu, self.b_mu, self.w_std, self.b_std]
+
+    def use_device_counter(self, enable=True):
+        """Keep the sampling counter in device memory so that CUDA-graph replays draw fresh noise."""
+        if enable and self._counter_dev is None:
+            self._counter_dev = torch.full((1,), self.counter, dtype=torch.int64, device=self.device)
+        elif not enable and self._counter_dev is not None:
+            self.counter = int(self._counter_dev.item())
+            self._counter_dev = None
 
     def act(self, obs, eps=None, want_moments=False, out=None):
         """``obs``: normalised observations (..., obs_size) on the device (e.g. the fused (B,A,S)
@@ -72,10 +88,13 @@ class FusedActor:
                 eps = eps.to(device=self.device, dtype=torch.float32).contiguous()
             self.counter += 1
             p = lambda t: t.data_ptr() if t is not None else None
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if self._counter_dev is not None:
+                self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
             _rollout_check(self._lib.marlnav_actor_sample_f32(
                 p(x), n, self.obs_size, self.hidden, p(self.w1), p(self.b1), p(self.w_mu), p(self.b_mu),
-                p(self.w_std), p(self.b_std), p(eps), self.seed, self.counter, p(actions), p(log_probs),
-                p(mu), p(var), torch.cuda.current_stream(self.device).cuda_stream), "marlnav_actor_sample_f32")
+                p(self.w_std), p(self.b_std), p(eps), self.seed, self.counter, p(self._counter_dev),
+                p(actions), p(log_probs), p(mu), p(var), stream), "marlnav_actor_sample_f32")
         return (actions, log_probs, mu, var) if want_moments else (actions, log_probs)
 
 
@@ -92,7 +111,13 @@ class FusedCritic:
     def refresh(self, critic):
         sd = critic if isinstance(critic, dict) else critic.state_dict()
         g = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
-        self.w1, self.b1, self.w2, self.b2 = g('fc1.weight'), g('fc1.bias'), g('fc2.weight'), g('fc2.bias')
+        new = [g('fc1.weight'), g('fc1.bias'), g('fc2.weight'), g('fc2.bias')]
+        old = getattr(self, 'w1', None)
+        if old is not None and all(o.shape == n.shape for o, n in zip([self.w1, self.b1, self.w2, self.b2], new)):
+            for o, n in zip([self.w1, self.b1, self.w2, self.b2], new):     # in place (CUDA graphs)
+                o.copy_(n)
+        else:
+            self.w1, self.b1, self.w2, self.b2 = new
         self.hidden, self.inputs = self.w1.shape
 
     def __call__(self, obs, out=None):
@@ -172,3 +197,33 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     buf['last_obs'] = obs_all[T]
     buf['done'] = torch.logical_or(term.view(torch.bool), trunc.view(torch.bool))   # models.py:119
     return buf
+
+
+class RolloutGraph:
+    """``collect_rollout`` captured once in a CUDA graph: a rollout of
+    ``buffer_len`` steps becomes one graph launch.  The environment's reset counter and the actor's
+    sampling counter live in device memory, so every replay continues the same random streams an
+    eager loop would use; ``FusedActor.refresh`` / ``FusedCritic.refresh`` update weights in place.
+    ``replay()`` returns the SAME buffer tensors every time (clone what must outlive the next replay)."""
+
+    def __init__(self, env, actor, buffer_len, critic=None, warmup_steps=2):
+        if critic is not None and not isinstance(critic, FusedCritic):
+            raise _lib.MarlnavError("RolloutGraph needs a FusedCritic (or no critic)")
+        self.env, self.actor, self.critic, self.buffer_len = env, actor, critic, int(buffer_len)
+        env.use_device_counter(True)
+        actor.use_device_counter(True)
+        dev = env.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            if warmup_steps:                                  # lazy kernel attributes, allocator warm-up
+                collect_rollout(env, actor, warmup_steps, critic=critic)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.buffers = collect_rollout(env, actor, self.buffer_len, critic=critic)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def replay(self):
+        self.graph.replay()
+        return self.buffers

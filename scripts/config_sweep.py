@@ -120,6 +120,14 @@ def rollout_line(B=1024, A=3, O=3, steps=1000):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         buf = mb.collect_rollout(env, fa, steps, critic=cr)
         torch.cuda.synchronize(); res[name] = B * steps / (time.perf_counter() - t0)
+    # the whole T-step rollout as ONE CUDA-graph launch (device-resident counters: every replay
+    # continues the eager random streams, tests/test_gpu_rollout.py)
+    rg = mb.RolloutGraph(env, fa, steps, critic=fcrit)
+    rg.replay(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        rg.replay()
+    torch.cuda.synchronize(); res["rollout_graph_actor_critic_env_steps_per_sec"] = 5 * B * steps / (time.perf_counter() - t0)
     for rep in range(2):                                   # second pass = warm
         torch.cuda.synchronize(); t0 = time.perf_counter()
         ret = mb.discounted_returns(buf['rewards'], buf['done'], 0.9, normalize=True)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.marlnav_abi_version() == 1
+    assert lib.marlnav_abi_version() == 2
     assert lib.marlnav_obs_size(3, 3) == 12 and lib.marlnav_obs_size(8, 16) == 48
     assert lib.marlnav_obs_size(1, 3) == 0 and lib.marlnav_obs_size(3, 0) == 0
     assert lib.marlnav_obs_size(27, 3) == 0
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from marlnav_b200 import _lib
     assert ctypes.sizeof(_lib.EnvParams) == 4 * 4 + 27 * 4
-    assert ctypes.sizeof(_lib.ResetSpec) == 3 * 8 + 3 * 8 + 8 + 3 * 8
+    assert ctypes.sizeof(_lib.ResetSpec) == 3 * 8 + 3 * 8 + 8 + 3 * 8 + 8
     assert ctypes.sizeof(_lib.IoTransform) == 4 * 8
     from oracle import oracle as orc
     assert ctypes.sizeof(orc.MoParams) == ctypes.sizeof(_lib.EnvParams)

@@ -115,3 +115,51 @@ def test_fused_critic_matches_torch(K, H, B):
     got = mb.FusedCritic(sd)(x.cuda()).cpu()
     assert got.shape == (B, 1)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=5e-6)
+
+
+def test_device_counter_mode_is_identical(oracle):
+    """Env.use_device_counter(): same results as the host-supplied counter, bit for bit."""
+    import marlnav_b200 as mb
+    from helpers import action_pool
+    p = mb.default_env_params(700, 3, 3, sampling_style='policy'); p['seed'] = 6
+    e_host, e_dev = mb.Env(dict(p)), mb.Env(dict(p))
+    e_dev.use_device_counter(True)
+    pool = action_pool(700, 3, angle=0.3)
+    for t in range(120):
+        a = pool[t % len(pool)].cuda()
+        o1, r1, t1, tr1 = e_host.step_fused(a)
+        o2, r2, t2, tr2 = e_dev.step_fused(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(t1, t2) and torch.equal(tr1, tr2)
+    assert torch.equal(e_host.obstacles, e_dev.obstacles) and e_host._num_col == e_dev._num_col > 0
+
+
+def test_rollout_graph_replays_continue_the_eager_streams():
+    """A captured rollout replayed twice == two eager collect_rollout calls (fresh reset positions
+    and fresh action noise on every replay), bit for bit."""
+    import marlnav_b200 as mb
+    B, A, O, T = 256, 3, 3, 60
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm, scal = dict(min_obs=lo, max_obs=hi), dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    w = _actor_weights()
+    g = torch.Generator().manual_seed(8)
+    fc1, fc2 = torch.nn.Linear(A * 12, 50), torch.nn.Linear(50, 1)
+    csd = {'fc1.weight': fc1.weight, 'fc1.bias': fc1.bias, 'fc2.weight': fc2.weight, 'fc2.bias': fc2.bias}
+
+    def make():
+        p = mb.default_env_params(B, A, O, sampling_style='policy', episode_len=25); p['seed'] = 12
+        env = mb.Env(p); env.fuse_io(norm, scal)
+        return env, mb.FusedActor(w, seed=3), mb.FusedCritic(csd)
+    env_e, act_e, cri_e = make()
+    mb.collect_rollout(env_e, act_e, 2, critic=cri_e)                 # RolloutGraph's warm-up, eagerly
+    eager = [mb.collect_rollout(env_e, act_e, T, critic=cri_e) for _ in range(2)]
+    env_g, act_g, cri_g = make()
+    rg = mb.RolloutGraph(env_g, act_g, T, critic=cri_g, warmup_steps=2)
+    for k in range(2):
+        buf = rg.replay()
+        torch.cuda.synchronize()
+        for key in ('obs', 'actions', 'log_probs', 'rewards', 'done', 'values'):
+            assert torch.equal(buf[key], eager[k][key]), (k, key)
+    assert not torch.equal(eager[0]['actions'], eager[1]['actions'])
+    assert torch.equal(env_g.states, env_e.states) and torch.equal(env_g.obstacles, env_e.obstacles)
