@@ -30,10 +30,11 @@ def test_fused_actor_matches_torch(oracle, S, H, N):
     act, lp, mu, var = fa.act(obs.cuda(), eps=eps, want_moments=True)
     r_act, r_lp, r_mu, r_var = oracle.actor_reference(obs, w, eps)
     # float32 dot products in a different association than torch's GEMM: 1e-5 relative
-    np.testing.assert_allclose(mu.cpu().numpy(), r_mu.numpy(), rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(var.cpu().numpy(), r_var.numpy(), rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(act.cpu().numpy(), r_act.numpy(), rtol=1e-5, atol=5e-6)
-    np.testing.assert_allclose(lp.cpu().numpy(), r_lp.numpy(), rtol=2e-5, atol=2e-5)
+    # (torch's CPU GEMM may also split its sums differently from run to run with MKL threading)
+    np.testing.assert_allclose(mu.cpu().numpy(), r_mu.numpy(), rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), r_var.numpy(), rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(act.cpu().numpy(), r_act.numpy(), rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(lp.cpu().numpy(), r_lp.numpy(), rtol=5e-5, atol=5e-5)
 
 
 def test_fused_actor_sampling_is_standard_normal_and_addressed():
