@@ -294,7 +294,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(A, O, B), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": algorithmic_bytes(A, O),
-                         "kernel": "mn::step_warp_kernel" if A < 4 else "mn::step_kernel",
+                         "kernel": ("mn::step_env_kernel" if (A, O) in ((3, 3), (3, 1)) else
+                                    "mn::step_team_kernel" if (A, O) == (8, 16) else "mn::step_kernel"),
                          "per": "one launch = one step of one GPU's slice"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes * world,

@@ -1,2 +1,2 @@
-TESTS=1 TMO=60 VARIANTS="N N2" bash scripts/gpu_ab.sh
-CFG="--agents 8 --obstacles 16 --envs 262144 --steps 300" TESTS=0 TMO=60 VARIANTS="N N2" bash scripts/gpu_ab.sh
+TESTS=1 TMO=60 VARIANTS="N2 N3 SYM" NCU=N3 bash scripts/gpu_ab.sh
+CFG="--agents 8 --obstacles 16 --envs 262144 --steps 300" TESTS=0 TMO=60 VARIANTS="N2 N3" bash scripts/gpu_ab.sh
