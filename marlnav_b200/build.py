@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     """Compile when the library is missing or older than its sources; returns its path."""
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
         return LIB
-    extra = os.environ.get("MARLNAV_NVCC_EXTRA", "").split()      # e.g. -DMN_W1_WARPS=5 for A/B builds
+    extra = os.environ.get("MARLNAV_NVCC_EXTRA", "").split()      # extra -D flags for A/B builds
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC, SRC2]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -51,6 +51,43 @@ def _run_free(params, oracle, steps, seed=11, angle=0.2, check_every=1):
     return ndone
 
 
+def _run_free_with_geometry(params, oracle, steps, geometry, seed=5):
+    """_run_free with the reference's hard-coded geometry constants (environment.py:56-68)
+    overridden on both sides: the launch then does not match the compiled-in division profile
+    and takes the kernels built with run-time division modes (IEEE / proven / power-of-two)."""
+    B, A = params['num_parallel'], params['num_agents']
+    env = _mk(params, seed)
+    oe = oracle.OracleEnv(cpu_params(params), seed=seed)
+    for k, v in geometry.items():
+        setattr(env._c_params, k, v)
+        setattr(oe.p, k, v)
+    pool = action_pool(B, A)
+    ndone = 0
+    for t in range(steps):
+        act = pool[t % len(pool)]
+        obs, rew, term, trunc = env.step_fused(act.cuda())
+        o_obs, o_rew, o_term, o_trunc = oe.step_fused(act.numpy())
+        tag = f"step {t}"
+        assert_bits_equal(f"{tag} terminated", term.cpu().numpy(), o_term)
+        assert_bits_equal(f"{tag} truncated", trunc.cpu().numpy(), o_trunc)
+        assert_bits_equal(f"{tag} rewards", rew.cpu().numpy(), o_rew)
+        assert_bits_equal(f"{tag} obs", obs.cpu().numpy(), o_obs)
+        ndone += int((o_term | o_trunc).sum())
+    _compare_state(env, oe, "final")
+    return ndone
+
+
+@pytest.mark.parametrize("geometry", [
+    dict(init_dist=1234.5, max_at_prop_d=3.0, bond_sharpness=2.0),      # proven / proven / power of two
+    dict(init_dist=1024.0, max_at_prop_d=1.0, bond_sharpness=0.7, ideal_dist=35.0, target_radius=45.0),
+])
+def test_custom_geometry_constants(oracle, geometry):
+    import marlnav_b200 as mb
+    ndone = _run_free_with_geometry(mb.default_env_params(1500, 3, 3, sampling_style='policy'), oracle, 150, geometry)
+    assert ndone > 100
+    _run_free_with_geometry(mb.template_env_params(300, 8, 16), oracle, 60, geometry)
+
+
 def test_triangle_3x3_free_running(oracle):
     import marlnav_b200 as mb
     ndone = _run_free(mb.default_env_params(4096, 3, 3, sampling_style='policy'), oracle, steps=320)
@@ -74,7 +111,7 @@ def test_scaled_scene_8x16(oracle):
     assert ndone > 50
 
 
-@pytest.mark.parametrize("A,O", [(2, 1), (2, 2), (4, 2), (5, 3), (3, 2), (9, 5), (16, 7), (26, 64)])
+@pytest.mark.parametrize("A,O", [(2, 1), (2, 2), (4, 2), (5, 3), (3, 2), (3, 4), (3, 5), (3, 6), (3, 7), (9, 5), (16, 7), (26, 64)])
 def test_generic_shapes(oracle, A, O):
     import marlnav_b200 as mb
     _run_free(mb.template_env_params(200 if A < 16 else 40, A, O), oracle, steps=40)
