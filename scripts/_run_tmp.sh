@@ -1,6 +1,2 @@
-python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 3 --prewarm-s 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('FIRST prewarm0', 'us_per_step', round(d['ms_per_step']*1000,2))"
-sleep 4
-python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 3 --prewarm-s 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('SECOND prewarm0', 'us_per_step', round(d['ms_per_step']*1000,2))"
-sleep 4
-python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('THIRD prewarm0.5', 'us_per_step', round(d['ms_per_step']*1000,2))"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+TESTS=1 TMO=60 VARIANTS="N3 N4" NCU=N4 bash scripts/gpu_ab.sh
+CFG="--agents 8 --obstacles 16 --envs 262144 --steps 300" TESTS=0 TMO=60 VARIANTS="N3 N4" bash scripts/gpu_ab.sh
