@@ -1,2 +1,5 @@
-TESTS=1 TMO=60 VARIANTS="N3 N4" NCU=N4 bash scripts/gpu_ab.sh
-CFG="--agents 8 --obstacles 16 --envs 262144 --steps 300" TESTS=0 TMO=60 VARIANTS="N3 N4" bash scripts/gpu_ab.sh
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+bash scripts/gpu_final_profiles.sh
