@@ -216,9 +216,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL
+        # printf its version banner there, and so does WARN; an explicit INFO/TRACE is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     A, O = args.agents, args.obstacles
