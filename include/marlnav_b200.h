@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MARLNAV_ABI_VERSION 2
+#define MARLNAV_ABI_VERSION 3
 #define MARLNAV_MAX_AGENTS 26     /* torch.cdist's direct formula holds up to 25 columns */
 #define MARLNAV_MAX_OBSTACLES 64
 
@@ -88,10 +88,12 @@ typedef struct marlnav_reset_spec {
     uint64_t seed;
     uint64_t step_counter;     /* 0 at construction, k for the k-th step() call */
     uint64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */
-    const uint64_t* step_counter_dev;  /* if non-NULL the kernels read the step counter from this DEVICE
-                                        * word instead of `step_counter`, so a captured CUDA graph draws
-                                        * fresh reset positions on every replay (bump it with
-                                        * marlnav_counter_add before each step) */
+    const uint64_t* step_counter_dev;  /* if non-NULL the kernels use `step_counter` + this DEVICE word
+                                        * (ABI 3), so a captured CUDA graph draws fresh reset positions
+                                        * on every replay: either bump the word with marlnav_counter_add
+                                        * before each step and pass step_counter = 0, or pass the step's
+                                        * 1-based index inside a batch of T steps and add T once after
+                                        * the batch */
 } marlnav_reset_spec;
 
 /* Optional fused caller-side transforms:
@@ -175,8 +177,9 @@ int marlnav_step_launch_info(const marlnav_env_params* params,
  *   actions = mu + sqrt(var)*eps;  log_probs = dist.log_prob(actions)
  * Weights are torch.nn.Linear layouts: w1 (H,S), b1 (H), w_mu/w_std (2,H), b_mu/b_std (2).
  * eps (N,2): standard-normal draws to use (parity tests) or NULL -> Philox4x32-10 + Box-Muller
- * addressed by (seed; row, counter); counter_dev, if non-NULL, overrides `counter` with a DEVICE
- * word (CUDA-graph replays).  mu_out/var_out (N,2) may be NULL. */
+ * addressed by (seed; row, counter); counter_dev, if non-NULL, is a DEVICE word added to `counter`
+ * (ABI 3; CUDA-graph replays, same convention as marlnav_reset_spec.step_counter_dev).
+ * mu_out/var_out (N,2) may be NULL. */
 int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H,
                              const float* w1, const float* b1, const float* w_mu, const float* b_mu,
                              const float* w_std, const float* b_std,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MARLNAV_B200_LIB may point at another build of the same ABI (A/B measurements only)
 LIB_PATH = os.environ.get("MARLNAV_B200_LIB") or os.path.join(_HERE, "libmarlnav_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/marlnav_b200.h declares
 EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",

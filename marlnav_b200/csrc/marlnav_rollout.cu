@@ -77,7 +77,7 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
     float e0, e1;
     if (eps) { e0 = eps[row * 2]; e1 = eps[row * 2 + 1]; }
     else {
-        if (counter_dev) counter = __ldg(counter_dev);
+        if (counter_dev) counter += __ldg(counter_dev);      // host value = offset inside a batch
         const uint4 r = philox4x32_10((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)counter,
                                       0x41435452u /* 'ACTR' */, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u1 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-08f;      // (0, 1]

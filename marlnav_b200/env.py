@@ -119,6 +119,8 @@ class Env(object):
         self._env_id_offset = int(params.get('env_id_offset', 0))
         self._reset_counter = 0
         self._counter_dev = None          # device-resident copy of the counter (use_device_counter)
+        self._counter_batch = False       # batch mode: steps pass their offset, one add per batch
+        self._counter_pending = 0
 
         self._c_params = self._make_c_params()
         self._setup_reset_source(params['init'])
@@ -212,7 +214,9 @@ class Env(object):
         rs.target_env_stride = 2 if per_env else 0
         rs.alias_first_step = 1 if alias else 0
         rs.flags = 1 if (not per_env and self._tmpl_nonneg) else 0      # MARLNAV_RESET_TMPL_NONNEG
-        rs.seed, rs.step_counter, rs.env_id_offset = self._seed, self._reset_counter, self._env_id_offset
+        rs.seed, rs.env_id_offset = self._seed, self._env_id_offset
+        # ABI 3: the kernels use step_counter + *step_counter_dev
+        rs.step_counter = self._reset_counter if self._counter_dev is None else self._counter_pending
         rs.step_counter_dev = self._counter_dev.data_ptr() if self._counter_dev is not None else None
         return rs
 
@@ -247,6 +251,33 @@ class Env(object):
     def sample_actions(self):
         return self._sampler()
 
+    def _advance_device_counter(self):
+        """The ``step_counter`` to pass for the step being launched (``_reset_counter`` was already
+        incremented).  Host counter: its value.  Device counter: 0 after bumping the device word, or,
+        in batch mode, the step's offset inside the batch (``flush_device_counter`` adds the total)."""
+        if self._counter_dev is None:
+            return self._reset_counter
+        if self._counter_batch:
+            self._counter_pending += 1
+            return self._counter_pending
+        self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1,
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+        return 0
+
+    def batch_device_counter(self, enable=True):
+        """Batch mode of the device-resident counter: steps address their Philox draws as
+        ``device word + offset`` and ONE ``marlnav_counter_add`` per batch replaces one per step
+        (``collect_rollout``: a third of the launches of a captured rollout)."""
+        if not enable:
+            self.flush_device_counter()
+        self._counter_batch = bool(enable) and self._counter_dev is not None
+
+    def flush_device_counter(self):
+        if self._counter_dev is not None and self._counter_pending:
+            self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), self._counter_pending,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        self._counter_pending = 0
+
     def use_device_counter(self, enable=True):
         """Keep the reset step counter in device memory (advanced by a one-thread kernel before
         every step) instead of passing it from the host.  Results are identical; the point is that
@@ -254,6 +285,7 @@ class Env(object):
         if enable and self._counter_dev is None:
             self._counter_dev = torch.full((1,), self._reset_counter, dtype=torch.int64, device=self.device)
         elif not enable and self._counter_dev is not None:
+            self.batch_device_counter(False)
             self._reset_counter = int(self._counter_dev.item())
             self._counter_dev = None
         self.__dict__.pop('_call_cache', None)
@@ -336,10 +368,7 @@ class Env(object):
             self._reset_counter += 1
             c = self._step_call_cache()
             rs = c['rs']
-            rs.step_counter = self._reset_counter
-            if self._counter_dev is not None:
-                self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1,
-                                              torch.cuda.current_stream(self.device).cuda_stream)
+            rs.step_counter = self._advance_device_counter()
             if self._alias_pending:
                 rs.alias_first_step = 1
             rc = c['fn'](c['p_ref'], c['rs_ref'], *c['fixed'], actions.data_ptr(),
@@ -402,9 +431,9 @@ class HostStepper:
             raise _lib.MarlnavError("HostStepper.step needs a contiguous float32 CPU tensor of shape (B,A,2)")
         with torch.cuda.device(env.device):
             env._reset_counter += 1
-            if env._counter_dev is not None:
-                env._lib.marlnav_counter_add(env._counter_dev.data_ptr(), 1, env._stream())
+            step_counter = env._advance_device_counter()
             rs = env._reset_spec(alias=env._alias_pending)
+            rs.step_counter = step_counter
             _lib.check(env._lib.marlnav_step_host_f32(
                 ctypes.byref(env._c_params), ctypes.byref(rs),
                 p(env.states), p(env.obstacles), p(env.target), p(env._step_num), p(env._terminates_u8),

@@ -38,6 +38,8 @@ class FusedActor:
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.counter = 0
         self._counter_dev = None
+        self._counter_batch = False        # see Env.batch_device_counter
+        self._counter_pending = 0
         self.w1 = None
         self.refresh(actor)
 
@@ -64,8 +66,21 @@ class FusedActor:
         if enable and self._counter_dev is None:
             self._counter_dev = torch.full((1,), self.counter, dtype=torch.int64, device=self.device)
         elif not enable and self._counter_dev is not None:
+            self.batch_device_counter(False)
             self.counter = int(self._counter_dev.item())
             self._counter_dev = None
+
+    def batch_device_counter(self, enable=True):
+        """Batch mode of the device-resident sampling counter (see ``Env.batch_device_counter``)."""
+        if not enable:
+            self.flush_device_counter()
+        self._counter_batch = bool(enable) and self._counter_dev is not None
+
+    def flush_device_counter(self):
+        if self._counter_dev is not None and self._counter_pending:
+            self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), self._counter_pending,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        self._counter_pending = 0
 
     def act(self, obs, eps=None, want_moments=False, out=None):
         """``obs``: normalised observations (..., obs_size) on the device (e.g. the fused (B,A,S)
@@ -89,11 +104,17 @@ class FusedActor:
             self.counter += 1
             p = lambda t: t.data_ptr() if t is not None else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
+            counter = self.counter              # ABI 3: the kernel uses counter + *counter_dev
             if self._counter_dev is not None:
-                self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
+                if self._counter_batch:
+                    self._counter_pending += 1
+                    counter = self._counter_pending
+                else:
+                    self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
+                    counter = 0
             _rollout_check(self._lib.marlnav_actor_sample_f32(
                 p(x), n, self.obs_size, self.hidden, p(self.w1), p(self.b1), p(self.w_mu), p(self.b_mu),
-                p(self.w_std), p(self.b_std), p(eps), self.seed, self.counter, p(self._counter_dev),
+                p(self.w_std), p(self.b_std), p(eps), self.seed, counter, p(self._counter_dev),
                 p(actions), p(log_probs), p(mu), p(var), stream), "marlnav_actor_sample_f32")
         return (actions, log_probs, mu, var) if want_moments else (actions, log_probs)
 
@@ -134,6 +155,16 @@ class FusedCritic:
                 self.w2.data_ptr(), self.b2.data_ptr(), v.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream), "marlnav_critic_value_f32")
         return v
+
+
+_CRITIC_STREAMS = {}
+
+
+def _critic_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _CRITIC_STREAMS:
+        _CRITIC_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _CRITIC_STREAMS[key]
 
 
 def discounted_returns(rewards, done, gamma, normalize=False):
@@ -183,16 +214,30 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     if critic is not None:
         buf['values'] = torch.empty(T, B, 1, device=dev)
     torch.div(env.observations_fused() - mean, scale, out=obs_all[0])          # models.py:110
+    # device-resident counters: each step passes its offset, ONE add per counter after the loop
+    env.batch_device_counter(True)
+    actor.batch_device_counter(True)
+    # The critic only reads obs_all[t] and writes values[t]: it runs on a forked stream, off the
+    # actor -> step critical path (in a captured graph: a parallel branch joined at the end).
+    main = torch.cuda.current_stream(dev)
+    side = _critic_stream(dev) if isinstance(critic, FusedCritic) else None
     for t in range(T):
         obs = obs_all[t]
-        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
-        if critic is not None:
-            if isinstance(critic, FusedCritic):
+        if side is not None:
+            ready = torch.cuda.Event()
+            ready.record(main)                                                  # obs_all[t] is complete
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
                 critic(obs.view(B, A * S), out=buf['values'][t])                # models.py:120
-            else:
-                buf['values'][t].copy_(critic(obs.view(B, A * S)))
+        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
+        if critic is not None and side is None:
+            buf['values'][t].copy_(critic(obs.view(B, A * S)))
         # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
         env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
+    if side is not None:
+        main.wait_stream(side)
+    env.batch_device_counter(False)
+    actor.batch_device_counter(False)
     buf['obs'] = obs_all[:T]
     buf['last_obs'] = obs_all[T]
     buf['done'] = torch.logical_or(term.view(torch.bool), trunc.view(torch.bool))   # models.py:119

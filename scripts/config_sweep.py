@@ -117,9 +117,12 @@ def rollout_line(B=1024, A=3, O=3, steps=1000):
     for name, cr in (("fused_actor_rollout_env_steps_per_sec", None), ("fused_actor_plus_torch_critic_env_steps_per_sec", critic),
                      ("fused_actor_plus_fused_critic_env_steps_per_sec", fcrit)):
         mb.collect_rollout(env, fa, 50, critic=cr)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        buf = mb.collect_rollout(env, fa, steps, critic=cr)
-        torch.cuda.synchronize(); res[name] = B * steps / (time.perf_counter() - t0)
+        best = 0.0
+        for _ in range(3):                                     # host-bound leg: best of three
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            buf = mb.collect_rollout(env, fa, steps, critic=cr)
+            torch.cuda.synchronize(); best = max(best, B * steps / (time.perf_counter() - t0))
+        res[name] = best
     # the whole T-step rollout as ONE CUDA-graph launch (device-resident counters: every replay
     # continues the eager random streams, tests/test_gpu_rollout.py)
     rg = mb.RolloutGraph(env, fa, steps, critic=fcrit)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.marlnav_abi_version() == 2
+    assert lib.marlnav_abi_version() == 3
     assert lib.marlnav_obs_size(3, 3) == 12 and lib.marlnav_obs_size(8, 16) == 48
     assert lib.marlnav_obs_size(1, 3) == 0 and lib.marlnav_obs_size(3, 0) == 0
     assert lib.marlnav_obs_size(27, 3) == 0
