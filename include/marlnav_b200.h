@@ -186,6 +186,28 @@ int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H,
                              const float* eps, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
                              float* actions, float* log_probs, float* mu_out, float* var_out, void* stream);
 
+/* The same actor as one struct, for the fused {actor -> step} launch. */
+typedef struct marlnav_actor_spec {
+    const float *w1, *b1, *w_mu, *b_mu, *w_std, *b_std;   /* device, torch.nn.Linear layouts as above */
+    int32_t S, H;                 /* obs_size (must equal the env's), hidden (<= 256) */
+    uint64_t seed, counter;       /* Philox addressing, as in marlnav_actor_sample_f32 */
+    const uint64_t* counter_dev;  /* optional DEVICE word added to `counter` */
+} marlnav_actor_spec;
+
+/* SURVEY.md section 8(f)-2, end state: MAPPO.get_data's inner iteration (models.py:113-122) as ONE
+ * launch -- actor forward + sample + log_prob on the normalised observations `obs_in` (B,A,S) of the
+ * current state, ActionScaler, the environment step, ObsNormalizer on the new observations.
+ * Writes actions_out (B*A,2) raw sampled actions, log_probs_out (B*A), and the step's outputs as
+ * marlnav_step_f32.  Requires `io` with both transforms and a team shape with a thread-per-env
+ * kernel (3 agents, 1..6 obstacles); returns MARLNAV_ERR_BAD_SHAPE otherwise (callers then use
+ * marlnav_actor_sample_f32 + marlnav_step_f32, which give the same bits). */
+int marlnav_act_step_f32(const marlnav_env_params* params, const marlnav_reset_spec* reset,
+                         float* states, float* obstacles, float* target, float* step_num, uint8_t* terminates,
+                         const marlnav_actor_spec* actor, const float* obs_in,
+                         float* actions_out, float* log_probs_out,
+                         float* obs, float* rewards, uint8_t* terminated, uint8_t* truncated,
+                         unsigned long long* stats, const marlnav_io_transform* io, void* stream);
+
 /* Critic.forward, marlnav/models.py:39-56: values (B) = fc2(relu(fc1(x))) for x = the env's
  * flattened normalised observations (K = A*S inputs, hidden H <= 64; reference: 36 -> 50 -> 1).
  * w1 (H,K), b1 (H), w2 (1,H), b2 (1) in torch.nn.Linear layout. */

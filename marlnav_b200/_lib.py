@@ -15,7 +15,7 @@ ABI_VERSION = 3
 # every symbol include/marlnav_b200.h declares
 EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",
            "marlnav_counter_add", "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
-           "marlnav_step_launch_info", "marlnav_actor_sample_f32", "marlnav_critic_value_f32",
+           "marlnav_step_launch_info", "marlnav_actor_sample_f32", "marlnav_act_step_f32", "marlnav_critic_value_f32",
            "marlnav_discounted_returns_f64",
            "marlnav_rollout_last_error")
 
@@ -51,6 +51,13 @@ class IoTransform(ctypes.Structure):
                 ("act_mean", ctypes.c_void_p), ("act_scale", ctypes.c_void_p)]
 
 
+class ActorSpec(ctypes.Structure):
+    """struct marlnav_actor_spec"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w1", "b1", "w_mu", "b_mu", "w_std", "b_std")] + \
+               [("S", ctypes.c_int32), ("H", ctypes.c_int32), ("seed", ctypes.c_uint64),
+                ("counter", ctypes.c_uint64), ("counter_dev", ctypes.c_void_p)]
+
+
 class MarlnavError(RuntimeError):
     pass
 
@@ -78,6 +85,7 @@ def load():
     lib.marlnav_observe_f32.argtypes = [vp] * 6
     lib.marlnav_init_f32.argtypes = [vp] * 8
     lib.marlnav_step_host_f32.argtypes = [vp] * 20
+    lib.marlnav_act_step_f32.argtypes = [vp] * 18
     lib.marlnav_obs_size.argtypes = [i32, i32]
     i64, u64, f64 = ctypes.c_longlong, ctypes.c_uint64, ctypes.c_double
     lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64] + [vp] * 6

@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "marlnav_kernels.cu")
 SRC2 = os.path.join(_HERE, "csrc", "marlnav_rollout.cu")
-DEPS = [SRC, SRC2, os.path.join(_HERE, "csrc", "marlnav_math.cuh"),
+DEPS = [SRC, SRC2, os.path.join(_HERE, "csrc", "marlnav_math.cuh"), os.path.join(_HERE, "csrc", "marlnav_actor.cuh"),
         os.path.join(os.path.dirname(_HERE), "include", "marlnav_b200.h")]
 LIB = os.path.join(_HERE, "libmarlnav_b200.so")
 

@@ -16,21 +16,9 @@
 #include <stdio.h>
 
 #include "../../include/marlnav_b200.h"
+#include "marlnav_actor.cuh"
 
 namespace mnr {
-
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
 
 // One thread per (env, agent) row.  The reference's Actor has NO activation after fc1
 // (models.py:29-31): h = fc1(x); mu = tanh(fc_mu(h)); "std" = softplus(fc_std(h)), and that
@@ -47,13 +35,7 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
                     float* __restrict__ actions, float* __restrict__ log_probs,
                     float* __restrict__ mu_out, float* __restrict__ var_out) {
     extern __shared__ float sm[];
-    float* s_w1 = sm;                    // (H,S)
-    float* s_b1 = s_w1 + H * S;          // (H)
-    float* s_wm = s_b1 + H;              // (2,H)
-    float* s_ws = s_wm + 2 * H;          // (2,H)
-    for (int i = threadIdx.x; i < H * S; i += blockDim.x) s_w1[i] = w1[i];
-    for (int i = threadIdx.x; i < H; i += blockDim.x) s_b1[i] = b1[i];
-    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) { s_wm[i] = w_mu[i]; s_ws[i] = w_std[i]; }
+    mna::stage_actor_weights(sm, S, H, w1, b1, w_mu, w_std, threadIdx.x, blockDim.x);
     __syncthreads();
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;
@@ -61,40 +43,12 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
     float x[MAX_S];
 #pragma unroll
     for (int k = 0; k < MAX_S; ++k) x[k] = k < S ? obs[row * S + k] : 0.f;
-    float m0 = b_mu[0], m1 = b_mu[1], v0 = b_std[0], v1 = b_std[1];
-    for (int j = 0; j < H; ++j) {
-        float h = s_b1[j];
-#pragma unroll
-        for (int k = 0; k < MAX_S; ++k)
-            if (k < S) h = fmaf(x[k], s_w1[j * S + k], h);
-        m0 = fmaf(h, s_wm[j], m0); m1 = fmaf(h, s_wm[H + j], m1);
-        v0 = fmaf(h, s_ws[j], v0); v1 = fmaf(h, s_ws[H + j], v1);
-    }
-    m0 = tanhf(m0); m1 = tanhf(m1);
-    v0 = v0 > 20.f ? v0 : log1pf(expf(v0));          // F.softplus, beta 1, threshold 20
-    v1 = v1 > 20.f ? v1 : log1pf(expf(v1));
-
-    float e0, e1;
-    if (eps) { e0 = eps[row * 2]; e1 = eps[row * 2 + 1]; }
-    else {
-        if (counter_dev) counter += __ldg(counter_dev);      // host value = offset inside a batch
-        const uint4 r = philox4x32_10((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)counter,
-                                      0x41435452u /* 'ACTR' */, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const float u1 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-08f;      // (0, 1]
-        const float u2 = (float)(r.y >> 8) * 5.9604644775390625e-08f;               // [0, 1)
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
-        e0 = rad * cs; e1 = rad * sn;
-    }
-    const float a0 = fmaf(sqrtf(v0), e0, m0), a1 = fmaf(sqrtf(v1), e1, m1);
-    actions[row * 2] = a0; actions[row * 2 + 1] = a1;
-    // MultivariateNormal(mu, diag(v)).log_prob(a), k = 2
-    const float d0 = a0 - m0, d1 = a1 - m1;
-    const float maha = d0 * d0 / v0 + d1 * d1 / v1;
-    log_probs[row] = -0.5f * maha - 0.5f * (logf(v0) + logf(v1)) - 1.8378770664093453f;
-    if (mu_out) { mu_out[row * 2] = m0; mu_out[row * 2 + 1] = m1; }
-    if (var_out) { var_out[row * 2] = v0; var_out[row * 2 + 1] = v1; }
+    if (counter_dev) counter += __ldg(counter_dev);      // host value = offset inside a batch
+    const mna::ActorOut o = mna::actor_row<MAX_S>(x, S, H, mna::ActorWeights(sm, S, H), b_mu, b_std, eps, seed, counter, row);
+    actions[row * 2] = o.a0; actions[row * 2 + 1] = o.a1;
+    log_probs[row] = o.logp;
+    if (mu_out) { mu_out[row * 2] = o.m0; mu_out[row * 2 + 1] = o.m1; }
+    if (var_out) { var_out[row * 2] = o.v0; var_out[row * 2 + 1] = o.v1; }
 }
 
 // Critic.forward (models.py:39-56): value = fc2(relu(fc1(flatten(x)))), one thread per env.
@@ -124,6 +78,40 @@ critic_value_kernel(const float* __restrict__ obs, long long B, int K, int H, co
     for (int j = 0; j < MAX_H; ++j)
         if (j < H) v = fmaf(fmaxf(h[j], 0.f), w2[j], v);
     values[e] = v;
+}
+
+// The same critic for SMALL batches (rollouts at the reference's scale, ~1 000 envs), where one
+// thread per env is a 1 800-step serial chain on a handful of warps: here 64 lanes share an env, one
+// hidden unit each (K steps), and one lane finishes the H-term output sum.  Same summation orders
+// as critic_value_kernel, hence the same bits.  4 envs in flight per CTA.
+template <int MAX_H>
+__global__ void __launch_bounds__(4 * MAX_H)
+critic_value_wide_kernel(const float* __restrict__ obs, long long B, int K, int H, const float* __restrict__ w1,
+                         const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                         float* __restrict__ values) {
+    extern __shared__ float sm[];
+    float* s_w1 = sm;                    // transposed to (K,H): lane j walks k with stride H, conflict-free
+    float* s_h = sm + (size_t)H * K;     // (4, MAX_H) relu(h)
+    for (int i = threadIdx.x; i < H * K; i += blockDim.x) { const int j = i / K, k = i - j * K; s_w1[k * H + j] = w1[i]; }
+    __syncthreads();
+    const int g = threadIdx.x / MAX_H, j = threadIdx.x % MAX_H;
+    const long long stride = (long long)gridDim.x * 4;
+    for (long long e0 = (long long)blockIdx.x * 4; e0 < B; e0 += stride) {      // uniform trip count per CTA
+        const long long e = e0 + g;
+        if (e < B && j < H) {
+            const float* x = obs + e * K;
+            float h = b1[j];
+            for (int k = 0; k < K; ++k) h = fmaf(__ldg(x + k), s_w1[k * H + j], h);
+            s_h[g * MAX_H + j] = fmaxf(h, 0.f);
+        }
+        __syncthreads();
+        if (e < B && j == 0) {
+            float v = b2[0];
+            for (int jj = 0; jj < H; ++jj) v = fmaf(s_h[g * MAX_H + jj], w2[jj], v);
+            values[e] = v;
+        }
+        __syncthreads();
+    }
 }
 
 // models.py:131-139, literally, in float64: curr = done ? 0 : rew + gamma * curr, backwards in t.
@@ -181,6 +169,17 @@ int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H, const 
     const long long grid = (N + threads - 1) / threads;
     const size_t smem = (size_t)(H * S + H + 4 * H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    {   // same shared-memory carveout as the step kernels it alternates with (no SM reconfiguration)
+        static bool carve[64] = {false};
+        int dev0 = 0; cudaGetDevice(&dev0);
+        if (!carve[dev0 & 63]) {
+            cudaFuncSetAttribute(mnr::actor_sample_kernel<16, 256>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(mnr::actor_sample_kernel<64, 256>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            carve[dev0 & 63] = true;
+        }
+    }
     if (S <= 16)
         mnr::actor_sample_kernel<16, 256><<<(unsigned)grid, threads, smem, st>>>(
             obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter,
@@ -203,6 +202,25 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
     if (K < 1 || H < 1 || H > 64 || (size_t)H * K * sizeof(float) > 200 * 1024) {
         snprintf(g_err2, sizeof g_err2, "marlnav_critic_value_f32: need hidden <= 64 and hidden*inputs*4 <= 200 KiB");
         return MARLNAV_ERR_BAD_SHAPE;
+    }
+    if (B <= 16384 && (size_t)(H * K + 4 * 64) * sizeof(float) <= 48 * 1024) {
+        // rollout-sized batches: 64 lanes per env (see critic_value_wide_kernel)
+        const long long want = (B + 3) / 4;
+        const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+        // same shared-memory carveout as the step kernels: SMs need not drain and reconfigure when
+        // this runs beside them on a forked stream (collect_rollout)
+        static bool carve[64] = {false};
+        int dev0 = 0; cudaGetDevice(&dev0);
+        if (!carve[dev0 & 63]) {
+            cudaFuncSetAttribute(mnr::critic_value_wide_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            carve[dev0 & 63] = true;
+        }
+        mnr::critic_value_wide_kernel<64><<<grid, 256, (size_t)(H * K + 4 * 64) * sizeof(float), (cudaStream_t)stream>>>(
+            obs, B, K, H, w1, b1, w2, b2, values);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { snprintf(g_err2, sizeof g_err2, "critic_value_wide launch: %s", cudaGetErrorString(e)); return (int)e; }
+        return 0;
     }
     const int threads = 128;
     const size_t smem = (size_t)H * K * sizeof(float);

@@ -251,6 +251,42 @@ class Env(object):
     def sample_actions(self):
         return self._sampler()
 
+    def supports_fused_actor(self, actor):
+        """Is there a fused {actor -> step} kernel for this env and actor (marlnav_act_step_f32)?"""
+        return (self.num_agents == 3 and 1 <= self.num_obstacles <= 6 and self._io is not None
+                and bool(self._io.obs_mean) and bool(self._io.act_scale)
+                and getattr(actor, 'obs_size', None) == self.obs_size and getattr(actor, 'hidden', 10 ** 9) <= 256
+                and getattr(getattr(actor, 'w1', None), 'device', None) == self.states.device)
+
+    def act_step_fused(self, actor, obs_in, out):
+        """``actor.act(obs_in)`` + ``step_fused`` as ONE launch (models.py:113-122).
+        ``obs_in`` (B,A,S): the normalised observations of the current state; ``out`` = preallocated
+        (actions (B*A,2), log_probs (B*A), next_obs (B,A,S), rewards (B), terminated_u8 (B),
+        truncated_u8 (B)).  Needs ``fuse_io`` with both transforms."""
+        if not self.supports_fused_actor(actor):
+            raise _lib.MarlnavError("no fused actor+step kernel for this env/actor (see supports_fused_actor)")
+        actions, log_probs, obs, rew, term, trunc = out
+        if obs_in.data_ptr() == obs.data_ptr():
+            raise _lib.MarlnavError("act_step_fused: obs_in and the output observations must be different buffers")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            sp = actor.spec(actor._advance_counter(stream))
+            self._reset_counter += 1
+            rs = self._reset_spec(alias=self._alias_pending)
+            rs.step_counter = self._advance_device_counter()
+            _lib.check(self._lib.marlnav_act_step_f32(
+                ctypes.byref(self._c_params), ctypes.byref(rs), self._ptr(self.states), self._ptr(self.obstacles),
+                self._ptr(self.target), self._ptr(self._step_num), self._ptr(self._terminates_u8),
+                ctypes.byref(sp), obs_in.data_ptr(), actions.data_ptr(), log_probs.data_ptr(),
+                obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), self._ptr(self._stats),
+                ctypes.byref(self._io), stream), "marlnav_act_step_f32")
+            if self._alias_pending:
+                # the reference's template froze at "state after the first move" (B-6)
+                self._tmpl_states = self.states.clone()
+                self._alias_pending = False
+                self.__dict__.pop('_call_cache', None)      # template pointer changed
+        return actions, log_probs, obs, rew, term, trunc
+
     def _advance_device_counter(self):
         """The ``step_counter`` to pass for the step being launched (``_reset_counter`` was already
         incremented).  Host counter: its value.  Device counter: 0 after bumping the device word, or,

@@ -70,6 +70,27 @@ class FusedActor:
             self.counter = int(self._counter_dev.item())
             self._counter_dev = None
 
+    def _advance_counter(self, stream):
+        """The ``counter`` argument for the launch being made (ABI 3: the kernels add the device word)."""
+        self.counter += 1
+        if self._counter_dev is None:
+            return self.counter
+        if self._counter_batch:
+            self._counter_pending += 1
+            return self._counter_pending
+        self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
+        return 0
+
+    def spec(self, counter):
+        """``marlnav_actor_spec`` of this actor for one fused {actor -> step} launch."""
+        sp = _lib.ActorSpec()
+        sp.w1, sp.b1 = self.w1.data_ptr(), self.b1.data_ptr()
+        sp.w_mu, sp.b_mu = self.w_mu.data_ptr(), self.b_mu.data_ptr()
+        sp.w_std, sp.b_std = self.w_std.data_ptr(), self.b_std.data_ptr()
+        sp.S, sp.H, sp.seed, sp.counter = self.obs_size, self.hidden, self.seed, counter
+        sp.counter_dev = self._counter_dev.data_ptr() if self._counter_dev is not None else None
+        return sp
+
     def batch_device_counter(self, enable=True):
         """Batch mode of the device-resident sampling counter (see ``Env.batch_device_counter``)."""
         if not enable:
@@ -101,17 +122,9 @@ class FusedActor:
             var = torch.empty(n, 2, device=self.device) if want_moments else None
             if eps is not None:
                 eps = eps.to(device=self.device, dtype=torch.float32).contiguous()
-            self.counter += 1
             p = lambda t: t.data_ptr() if t is not None else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            counter = self.counter              # ABI 3: the kernel uses counter + *counter_dev
-            if self._counter_dev is not None:
-                if self._counter_batch:
-                    self._counter_pending += 1
-                    counter = self._counter_pending
-                else:
-                    self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
-                    counter = 0
+            counter = self._advance_counter(stream)
             _rollout_check(self._lib.marlnav_actor_sample_f32(
                 p(x), n, self.obs_size, self.hidden, p(self.w1), p(self.b1), p(self.w_mu), p(self.b_mu),
                 p(self.w_std), p(self.b_std), p(eps), self.seed, counter, p(self._counter_dev),
@@ -189,7 +202,8 @@ def discounted_returns(rewards, done, gamma, normalize=False):
 
 
 @torch.no_grad()
-def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None, scaler_params=None):
+def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None, scaler_params=None,
+                    fuse_actor=True):
     """``MAPPO.get_data`` (models.py:106-129) on device-resident buffers.
 
     ``env``: a ``marlnav_b200.Env``; ``actor``: a ``FusedActor``; ``critic``: optional ``FusedCritic``
@@ -197,7 +211,11 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     normaliser / action scaler fused in (``env.fuse_io``); pass the reference's ``normalizer`` /
     ``scaler`` param dicts here to do that.  Returns a dict of tensors with a leading time axis:
     ``obs (T,B,A,S)``, ``actions (T,B*A,2)``, ``log_probs (T,B*A)``, ``rewards (T,B)``, ``done (T,B)``
-    and ``values (T,B,1)`` when a critic is given."""
+    and ``values (T,B,1)`` when a critic is given.
+
+    ``fuse_actor``: sample the actions inside the step launch (``marlnav_act_step_f32``: one launch
+    per iteration instead of two) where that kernel exists -- 3 agents, 1..6 obstacles; same bits
+    either way (``test_fused_actor_step_matches_two_launches``)."""
     if normalizer_params is not None or scaler_params is not None:
         env.fuse_io(normalizer_params, scaler_params)
     if env._io is None or not env._io.obs_mean or not env._io.act_scale:
@@ -221,6 +239,7 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     # actor -> step critical path (in a captured graph: a parallel branch joined at the end).
     main = torch.cuda.current_stream(dev)
     side = _critic_stream(dev) if isinstance(critic, FusedCritic) else None
+    fused = bool(fuse_actor) and env.supports_fused_actor(actor)
     for t in range(T):
         obs = obs_all[t]
         if side is not None:
@@ -229,9 +248,14 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
             side.wait_event(ready)
             with torch.cuda.stream(side):
                 critic(obs.view(B, A * S), out=buf['values'][t])                # models.py:120
-        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
         if critic is not None and side is None:
             buf['values'][t].copy_(critic(obs.view(B, A * S)))
+        if fused:
+            # models.py:113-118,122 in one launch: sample from obs, scale, step, normalise
+            env.act_step_fused(actor, obs, out=(buf['actions'][t], buf['log_probs'][t], obs_all[t + 1],
+                                                buf['rewards'][t], term[t], trunc[t]))
+            continue
+        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
         # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
         env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
     if side is not None:

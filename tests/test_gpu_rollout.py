@@ -103,6 +103,34 @@ def test_collect_rollout_matches_stepwise_loop(oracle):
     assert ret.shape == (T, B) and ret.dtype == torch.float64 and bool(torch.isfinite(ret).all())
 
 
+@pytest.mark.parametrize("B,O,H", [(515, 3, 50), (64, 1, 7), (300, 4, 64)])
+def test_fused_actor_step_matches_two_launches(B, O, H):
+    """marlnav_act_step_f32 (actor sampled inside the step launch) == marlnav_actor_sample_f32 followed
+    by marlnav_step_f32: every buffer of the rollout and the final env state, bit for bit."""
+    import marlnav_b200 as mb
+    A, T = 3, 70
+    S = 2 + 2 * O + 2 * (A - 1)
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm, scal = dict(min_obs=lo, max_obs=hi), dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    w = _actor_weights(S, H)
+    bufs, envs = [], []
+    for fuse in (True, False):
+        p = mb.default_env_params(B, A, O, sampling_style='policy', episode_len=30); p['seed'] = 21
+        env = mb.Env(p)
+        env.fuse_io(norm, scal)
+        fa = mb.FusedActor(w, seed=9)
+        assert env.supports_fused_actor(fa)
+        bufs.append(mb.collect_rollout(env, fa, T, fuse_actor=fuse))
+        envs.append(env)
+    for key in ('obs', 'last_obs', 'actions', 'log_probs', 'rewards', 'done'):
+        assert torch.equal(bufs[0][key], bufs[1][key]), key
+    assert bool(bufs[0]['done'].any())
+    assert torch.equal(envs[0].states, envs[1].states) and torch.equal(envs[0].obstacles, envs[1].obstacles)
+    assert (envs[0]._num_trunc, envs[0]._num_col) == (envs[1]._num_trunc, envs[1]._num_col)
+
+
 @pytest.mark.parametrize("K,H,B", [(36, 50, 1024), (384, 50, 300), (16, 7, 5)])
 def test_fused_critic_matches_torch(K, H, B):
     """Critic.forward (models.py:39-56) as one kernel vs the torch module."""
