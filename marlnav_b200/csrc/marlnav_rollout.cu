@@ -114,6 +114,50 @@ critic_value_wide_kernel(const float* __restrict__ obs, long long B, int K, int 
     }
 }
 
+// Mid-sized batches: L = 16 or 4 lanes per env inside one warp, each lane owning the hidden units
+// j = l, l + L, ... (independent K-step chains), lane 0 of the group finishing the H-term sum.
+// Same summation orders again.
+template <int L, int MAX_H>
+__global__ void __launch_bounds__(128)
+critic_value_group_kernel(const float* __restrict__ obs, long long B, int K, int H, const float* __restrict__ w1,
+                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                          float* __restrict__ values) {
+    constexpr int PER = (MAX_H + L - 1) / L;             // hidden units per lane
+    constexpr int GROUPS = 128 / L;                      // envs in flight per CTA
+    extern __shared__ float sm[];
+    float* s_w1 = sm;                                    // transposed to (K,H)
+    float* s_h = sm + (size_t)H * K;                     // (GROUPS, MAX_H) relu(h)
+    for (int i = threadIdx.x; i < H * K; i += blockDim.x) { const int j = i / K, k = i - j * K; s_w1[k * H + j] = w1[i]; }
+    __syncthreads();
+    const int g = threadIdx.x / L, l = threadIdx.x % L;
+    const long long stride = (long long)gridDim.x * GROUPS;
+    for (long long e0 = (long long)blockIdx.x * GROUPS; e0 < B; e0 += stride) {     // uniform trip count per CTA
+        const long long e = e0 + g;
+        if (e < B) {
+            const float* x = obs + e * K;
+            float h[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) h[u] = (l + u * L) < H ? b1[l + u * L] : 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float xk = __ldg(x + k);
+#pragma unroll
+                for (int u = 0; u < PER; ++u)
+                    if ((l + u * L) < H) h[u] = fmaf(xk, s_w1[k * H + l + u * L], h[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < PER; ++u)
+                if ((l + u * L) < H) s_h[g * MAX_H + l + u * L] = fmaxf(h[u], 0.f);
+        }
+        __syncwarp();
+        if (e < B && l == 0) {
+            float v = b2[0];
+            for (int jj = 0; jj < H; ++jj) v = fmaf(s_h[g * MAX_H + jj], w2[jj], v);
+            values[e] = v;
+        }
+        __syncwarp();
+    }
+}
+
 // models.py:131-139, literally, in float64: curr = done ? 0 : rew + gamma * curr, backwards in t.
 // (T,B) row-major: for a fixed t consecutive threads touch consecutive envs.
 __global__ void discounted_returns_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ done,
@@ -203,7 +247,31 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
         snprintf(g_err2, sizeof g_err2, "marlnav_critic_value_f32: need hidden <= 64 and hidden*inputs*4 <= 200 KiB");
         return MARLNAV_ERR_BAD_SHAPE;
     }
-    if (B <= 16384 && (size_t)(H * K + 4 * 64) * sizeof(float) <= 48 * 1024) {
+    if (B > 2048 && B <= 262144 && (size_t)(H * K + 32 * 64) * sizeof(float) <= 48 * 1024) {
+        // mid-sized batches: 16 or 4 lanes per env (see critic_value_group_kernel)
+        static bool carve[64] = {false};
+        int dev0 = 0; cudaGetDevice(&dev0);
+        if (!carve[dev0 & 63]) {
+            cudaFuncSetAttribute(mnr::critic_value_group_kernel<16, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(mnr::critic_value_group_kernel<4, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            carve[dev0 & 63] = true;
+        }
+        const bool l16 = B <= 32768;
+        const int groups = l16 ? 8 : 32;
+        const long long want = (B + groups - 1) / groups;
+        const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+        const size_t smem = (size_t)(H * K + groups * 64) * sizeof(float);
+        if (l16)
+            mnr::critic_value_group_kernel<16, 64><<<grid, 128, smem, (cudaStream_t)stream>>>(obs, B, K, H, w1, b1, w2, b2, values);
+        else
+            mnr::critic_value_group_kernel<4, 64><<<grid, 128, smem, (cudaStream_t)stream>>>(obs, B, K, H, w1, b1, w2, b2, values);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { snprintf(g_err2, sizeof g_err2, "critic_value_group launch: %s", cudaGetErrorString(e)); return (int)e; }
+        return 0;
+    }
+    if (B <= 2048 && (size_t)(H * K + 4 * 64) * sizeof(float) <= 48 * 1024) {
         // rollout-sized batches: 64 lanes per env (see critic_value_wide_kernel)
         const long long want = (B + 3) / 4;
         const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);

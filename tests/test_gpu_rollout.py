@@ -131,7 +131,7 @@ def test_fused_actor_step_matches_two_launches(B, O, H):
     assert (envs[0]._num_trunc, envs[0]._num_col) == (envs[1]._num_trunc, envs[1]._num_col)
 
 
-@pytest.mark.parametrize("K,H,B", [(36, 50, 1024), (384, 50, 300), (16, 7, 5)])
+@pytest.mark.parametrize("K,H,B", [(36, 50, 1024), (384, 50, 300), (16, 7, 5), (36, 50, 5000), (36, 64, 40001), (72, 33, 2049)])
 def test_fused_critic_matches_torch(K, H, B):
     """Critic.forward (models.py:39-56) as one kernel vs the torch module."""
     import marlnav_b200 as mb
