@@ -131,15 +131,17 @@ def rollout_line(B=1024, A=3, O=3, steps=1000):
     for _ in range(5):
         rg.replay()
     torch.cuda.synchronize(); res["rollout_graph_actor_critic_env_steps_per_sec"] = 5 * B * steps / (time.perf_counter() - t0)
-    for rep in range(2):                                   # second pass = warm
+    best_ours, best_ref = float('inf'), float('inf')
+    for rep in range(3):                                   # host-timed: best of three
         torch.cuda.synchronize(); t0 = time.perf_counter()
         ret = mb.discounted_returns(buf['rewards'], buf['done'], 0.9, normalize=True)
-        torch.cuda.synchronize(); res["discounted_returns_ms_T1000"] = 1e3 * (time.perf_counter() - t0)
+        torch.cuda.synchronize(); best_ours = min(best_ours, 1e3 * (time.perf_counter() - t0))
         t0 = time.perf_counter()
         curr = torch.zeros(B, dtype=float, device='cuda')
         for i in range(steps - 1, -1, -1):                 # the reference's loop, models.py:135-139
             curr = torch.where(buf['done'][i], 0., buf['rewards'][i] + 0.9 * curr)
-        torch.cuda.synchronize(); res["reference_return_loop_ms_T1000"] = 1e3 * (time.perf_counter() - t0)
+        torch.cuda.synchronize(); best_ref = min(best_ref, 1e3 * (time.perf_counter() - t0))
+    res["discounted_returns_ms_T1000"], res["reference_return_loop_ms_T1000"] = best_ours, best_ref
     return {"config": f"rollout {B}x{A}x{O} with actor in the loop (BASELINE configs[1])", **res}
 
 
