@@ -53,6 +53,25 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert g.value * e.value >= 1048576 and b.value % 32 == 0 and s.value < 227 * 1024
 
 
+def test_fused_actor_step_argument_errors_and_small_batch_geometry():
+    """marlnav_act_step_f32 validates before it launches; a small batch of the reference's team is
+    laid out thread-per-agent (8 envs per one-warp CTA), a large one thread-per-env (32)."""
+    from marlnav_b200 import _lib
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.ActorSpec) == 6 * 8 + 2 * 4 + 2 * 8 + 8
+    p = _lib.EnvParams(); p.num_envs, p.num_agents, p.num_obstacles = 64, 3, 3
+    rs = _lib.ResetSpec(); rs.alias_first_step = 1
+    rc = lib.marlnav_act_step_f32(ctypes.byref(p), ctypes.byref(rs), *([None] * 16))
+    assert rc == -1 and b"NULL" in lib.marlnav_last_error()
+    g, b, s, e = (ctypes.c_int() for _ in range(4))
+    info = lambda: lib.marlnav_step_launch_info(ctypes.byref(p), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s), ctypes.byref(e))
+    assert info() == 0 and (g.value, b.value, e.value) == (8, 32, 8)
+    p.num_envs = 1 << 20
+    assert info() == 0 and (g.value, b.value, e.value) == (1 << 15, 32, 32)
+    p.num_agents, p.num_obstacles, p.num_envs = 8, 16, 4096
+    assert info() == 0 and (g.value, b.value, e.value) == (1024, 32, 4)
+
+
 def test_env_refuses_cpu_device():
     import marlnav_b200 as mb
     with pytest.raises(mb.MarlnavError, match="no CPU fallback"):
