@@ -162,6 +162,42 @@ def test_device_counter_mode_is_identical(oracle):
     assert torch.equal(e_host.obstacles, e_dev.obstacles) and e_host._num_col == e_dev._num_col > 0
 
 
+@pytest.mark.parametrize("B", [300, 40000])
+def test_cuda_graph_of_back_to_back_steps_matches_eager(B):
+    """Plain step launches carry the programmatic-dependent-launch attribute; captured back to back
+    (device counter in batch mode: no kernel in between) they become programmatic graph edges.
+    Replays must equal the eager loop, resets included."""
+    import marlnav_b200 as mb
+    from helpers import action_pool
+    T = 64
+    p = mb.default_env_params(B, 3, 3, sampling_style='policy', episode_len=25); p['seed'] = 31
+    pool = [a.cuda() for a in action_pool(B, 3, angle=0.3)]
+    eager = mb.Env(dict(p))
+    ref = [[t.clone() for t in eager.step_fused(pool[i % len(pool)])] for i in range(2 * T)]
+    env = mb.Env(dict(p))
+    env.use_device_counter(True)
+    outs = [env._alloc_outputs() for _ in range(T)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            env.batch_device_counter(True)
+            for i in range(T):
+                env.step_fused(pool[i % len(pool)], out=outs[i])
+            env.batch_device_counter(False)
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(2):                       # T is a multiple of the pool length: same actions per replay
+        g.replay()
+        torch.cuda.synchronize()
+        for i in range(T):
+            o, r, te, tr = outs[i]
+            ro, rr, rte, rtr = ref[k * T + i]
+            assert torch.equal(o, ro) and torch.equal(r, rr), (k, i)
+            assert torch.equal(te.view(torch.bool), rte) and torch.equal(tr.view(torch.bool), rtr), (k, i)
+    assert torch.equal(env.states, eager.states) and torch.equal(env.obstacles, eager.obstacles)
+
+
 def test_rollout_graph_replays_continue_the_eager_streams():
     """A captured rollout replayed twice == two eager collect_rollout calls (fresh reset positions
     and fresh action noise on every replay), bit for bit."""
