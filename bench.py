@@ -112,11 +112,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(s), "reasons": sorted(self.reasons)}
 
 
-def make_action_pool(B, A, n, device, seed=1234):
+def make_action_pool(B, A, n, device, seed=1234, angle=0.2):
+    """turn angle ~ U(-angle, angle) -- 0.2 rad = "policy-like" (agents make
+    progress, collide, reset), pi = trig stress -- and acceleration ~ U(-0.5, 0.5)."""
     g = torch.Generator().manual_seed(seed)
     pool = []
     for _ in range(n):
-        ang = (torch.rand(B, A, generator=g) * 2 - 1) * 0.2
+        ang = (torch.rand(B, A, generator=g) * 2 - 1) * angle
         acc = (torch.rand(B, A, generator=g) * 2 - 1) * 0.5
         pool.append(torch.stack([ang, acc], dim=2).contiguous().to(device))
     return pool
@@ -196,7 +198,7 @@ def workload_config(args, B_local):
                         "random policy-like actions, auto-reset, episode_len 200 "
                         "(BASELINE.json configs[3]; configs[4] with --agents 8 --obstacles 16)",
             "envs_per_gpu": B_local, "num_agents": args.agents, "num_obstacles": args.obstacles,
-            "action_pool": 16, "prewarm": f"{args.prewarm_s} s of device copies before the warm-up steps",
+            "action_pool": 16, "action_angle_range": args.angle, "prewarm": f"{args.prewarm_s} s of device copies before the warm-up steps",
             "l2_policy": "working set per step (states+actions+obs) exceeds the 126 MB L2"
             if B_local * algorithmic_bytes(args.agents, args.obstacles) > 2 * 126e6 else
             "working set may fit in L2 -- not an HBM number"}
@@ -226,7 +228,7 @@ def run_ours(args):
     B = args.envs if args.scaling == "weak" else mb.shard_bounds(args.envs, rank, world)[1]
     offset = rank * B if args.scaling == "weak" else mb.shard_bounds(args.envs, rank, world)[0]
     env = mb.Env(env_params(B, A, O, f"cuda:{local_rank}", offset))
-    pool = make_action_pool(B, A, 16, dev)
+    pool = make_action_pool(B, A, 16, dev, angle=args.angle)
     out = env._alloc_outputs()          # steady-state callers reuse or recycle output tensors
     K, W = args.steps, max(args.warmup, 3)
 
@@ -338,6 +340,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--angle", type=float, default=0.2,
+                    help="turn-angle range of the random actions in rad (SURVEY 8d: 0.2 policy-like, 3.14159 trig stress)")
     ap.add_argument("--prewarm-s", type=float, default=0.5,
                     help="seconds of device copies before the warm-up steps (P-state ramp)")
     args = ap.parse_args()
