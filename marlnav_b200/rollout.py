@@ -223,7 +223,8 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     B, A, S, T = env.num_parallel, env.num_agents, env.obs_size, int(buffer_len)
     dev = env.device
     mean, scale = env._io_tensors[0], env._io_tensors[1]
-    # every kernel writes straight into its slice of the buffers: two launches per step
+    # every kernel writes straight into its slice of the buffers: one launch per step on the main
+    # stream (two where there is no fused actor kernel), the critic beside it
     obs_all = torch.empty(T + 1, B, A, S, device=dev)
     term = torch.empty(T, B, dtype=torch.uint8, device=dev)
     trunc = torch.empty(T, B, dtype=torch.uint8, device=dev)
@@ -240,28 +241,30 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
     main = torch.cuda.current_stream(dev)
     side = _critic_stream(dev) if isinstance(critic, FusedCritic) else None
     fused = bool(fuse_actor) and env.supports_fused_actor(actor)
-    for t in range(T):
-        obs = obs_all[t]
+    try:
+        for t in range(T):
+            obs = obs_all[t]
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(main)                                              # obs_all[t] is complete
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    critic(obs.view(B, A * S), out=buf['values'][t])            # models.py:120
+            if critic is not None and side is None:
+                buf['values'][t].copy_(critic(obs.view(B, A * S)))
+            if fused:
+                # models.py:113-118,122 in one launch: sample from obs, scale, step, normalise
+                env.act_step_fused(actor, obs, out=(buf['actions'][t], buf['log_probs'][t], obs_all[t + 1],
+                                                    buf['rewards'][t], term[t], trunc[t]))
+                continue
+            actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
+            # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
+            env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
+    finally:
         if side is not None:
-            ready = torch.cuda.Event()
-            ready.record(main)                                                  # obs_all[t] is complete
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                critic(obs.view(B, A * S), out=buf['values'][t])                # models.py:120
-        if critic is not None and side is None:
-            buf['values'][t].copy_(critic(obs.view(B, A * S)))
-        if fused:
-            # models.py:113-118,122 in one launch: sample from obs, scale, step, normalise
-            env.act_step_fused(actor, obs, out=(buf['actions'][t], buf['log_probs'][t], obs_all[t + 1],
-                                                buf['rewards'][t], term[t], trunc[t]))
-            continue
-        actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
-        # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
-        env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
-    if side is not None:
-        main.wait_stream(side)
-    env.batch_device_counter(False)
-    actor.batch_device_counter(False)
+            main.wait_stream(side)
+        env.batch_device_counter(False)             # (adds the pending totals to the device words)
+        actor.batch_device_counter(False)
     buf['obs'] = obs_all[:T]
     buf['last_obs'] = obs_all[T]
     buf['done'] = torch.logical_or(term.view(torch.bool), trunc.view(torch.bool))   # models.py:119
