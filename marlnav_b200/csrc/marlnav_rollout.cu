@@ -18,6 +18,10 @@
 #include "../../include/marlnav_b200.h"
 #include "marlnav_actor.cuh"
 
+#ifndef MARLNAV_CRITIC_GROUP_CTAS_PER_SM
+#define MARLNAV_CRITIC_GROUP_CTAS_PER_SM 4
+#endif
+
 namespace mnr {
 
 // One thread per (env, agent) row.  The reference's Actor has NO activation after fc1
@@ -261,7 +265,9 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
         const bool l16 = B <= 32768;
         const int groups = l16 ? 8 : 32;
         const long long want = (B + groups - 1) / groups;
-        const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+        // few enough CTAs that the per-CTA weight staging amortises over several env groups
+        const long long cap = 148 * MARLNAV_CRITIC_GROUP_CTAS_PER_SM;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
         const size_t smem = (size_t)(H * K + groups * 64) * sizeof(float);
         if (l16)
             mnr::critic_value_group_kernel<16, 64><<<grid, 128, smem, (cudaStream_t)stream>>>(obs, B, K, H, w1, b1, w2, b2, values);
