@@ -299,3 +299,50 @@ class RolloutGraph:
     def replay(self):
         self.graph.replay()
         return self.buffers
+
+
+class StepGraph:
+    """``len(actions)`` back-to-back fused steps captured in ONE CUDA graph (SURVEY.md section 8(e):
+    a rank that owns 1/8 of the batch steps it in ~12 us, less than a ctypes call + launch from
+    Python, so an eager loop is bound by the host).  The reset counter lives in device memory in
+    batch mode -- the captured steps pass their offset 1..K and the word is bumped once per replay --
+    so every replay draws the reset positions an eager loop would draw
+    (``test_cuda_graph_of_back_to_back_steps_matches_eager``).
+
+    ``actions``: a list of (B,A,2) device tensors (or one (K,B,A,2) tensor); they are read at
+    replay time, so a policy can refill them between replays.  ``keep_outputs=True`` gives every
+    step its own (obs, rewards, terminated, truncated) buffers (``.outputs[k]``); otherwise the K
+    steps write into one set (``.outputs[0]`` holds the last step's results)."""
+
+    def __init__(self, env, actions, keep_outputs=False):
+        self.env = env
+        self.actions = list(actions)
+        K = len(self.actions)
+        if K < 1:
+            raise _lib.MarlnavError("StepGraph needs at least one action tensor")
+        dev = env.device
+        env.use_device_counter(True)
+        n_out = K if keep_outputs else 1
+        self.outputs = [env._alloc_outputs() for _ in range(n_out)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            env.step_fused(self.actions[0], out=self.outputs[0])      # lazy kernel attributes, aliasing quirk B-6
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                env.batch_device_counter(True)
+                try:
+                    for k in range(K):
+                        env.step_fused(self.actions[k], out=self.outputs[k % n_out])
+                finally:
+                    env.batch_device_counter(False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.steps = K
+        env._reset_counter -= K            # the capture advanced the host mirror; nothing ran yet
+
+    def replay(self):
+        """Run the K captured steps on the current stream; returns ``.outputs``."""
+        self.graph.replay()
+        self.env._reset_counter += self.steps          # host mirror of the device word
+        return self.outputs

@@ -228,3 +228,33 @@ def test_rollout_graph_replays_continue_the_eager_streams():
             assert torch.equal(buf[key], eager[k][key]), (k, key)
     assert not torch.equal(eager[0]['actions'], eager[1]['actions'])
     assert torch.equal(env_g.states, env_e.states) and torch.equal(env_g.obstacles, env_e.obstacles)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,keep", [(96, True), (20000, False)])
+def test_step_graph_replays_continue_the_eager_loop(B, keep):
+    """marlnav_b200.StepGraph (K captured steps, batched device counter) replayed twice == 2K eager
+    steps, bit for bit; thread-per-agent (small batch) and thread-per-env (large batch) kernels."""
+    import marlnav_b200 as mb
+    from helpers import action_pool
+    p = mb.default_env_params(B, 3, 3, sampling_style='policy', episode_len=25); p['seed'] = 77
+    pool = [a.cuda() for a in action_pool(B, 3, angle=0.3)]
+    K = 2 * len(pool)
+    acts = [pool[i % len(pool)] for i in range(K)]
+    eager = mb.Env(dict(p))
+    seq = [acts[0]] + acts + acts                         # StepGraph's warm-up step runs acts[0] once
+    ref = [[t.clone() for t in eager.step_fused(a)] for a in seq]
+    env = mb.Env(dict(p))
+    sg = mb.StepGraph(env, acts, keep_outputs=keep)
+    for k in range(2):
+        outs = sg.replay()
+        torch.cuda.synchronize()
+        steps = range(K) if keep else [K - 1]
+        for i in steps:
+            o, r, te, tr = outs[i if keep else 0]
+            ro, rr, rte, rtr = ref[1 + k * K + i]
+            assert torch.equal(o, ro) and torch.equal(r, rr), (k, i)
+            assert torch.equal(te.view(torch.bool), rte) and torch.equal(tr.view(torch.bool), rtr), (k, i)
+    assert torch.equal(env.states, eager.states) and torch.equal(env.obstacles, eager.obstacles)
+    env.use_device_counter(False)
+    assert env._reset_counter == eager._reset_counter
