@@ -469,6 +469,14 @@ def actor_reference(obs, weights, eps):
     return actions, dist.log_prob(actions), mu, var
 
 
+def critic_reference(obs, weights):
+    """Critic.forward (models.py:52-56) with the same torch ops: flatten, fc1, relu, fc2."""
+    import torch
+    x = obs.reshape(obs.shape[0], -1)
+    h = torch.relu(torch.nn.functional.linear(x, weights['fc1.weight'], weights['fc1.bias']))
+    return torch.nn.functional.linear(h, weights['fc2.weight'], weights['fc2.bias'])
+
+
 def discounted_returns_reference(rewards, done, gamma):
     """models.py:131-139 restated with the same torch ops (float64 accumulator, torch.where)."""
     import torch

@@ -154,6 +154,110 @@ def scenario_case(name, sn, patched):
     save(name, dict(sn=sn, steps=1000), rec)
 
 
+def snm1_case(name, seed, patched):
+    """BASELINE.json configs[0], the literal `python -m marlnav -rc -sn -1 -se 0` setup
+    (__main__.py:129-138, utils.py:217-222,237-243): triangle initialiser + ConstantSampler
+    (action [0, 1] for every agent: cos = 1, sin = 0 exactly on any backend), B = 2, 1000 steps,
+    through the reference's own set_params(); only the Philox reset sampler (and, for the
+    patched set, acos) is injected.  The agents fly straight at the target, so this is the one
+    scenario with target reaches in free running (delayed termination, Appendix B-1)."""
+    args = refload.reference_args(sampler_num=-1)
+    ctx = refload.oracle_trig() if patched else torch.no_grad()
+    with ctx:
+        params = copy.deepcopy(utils_mod.set_params(args)['env'])
+        env = env_mod.Env(params)
+        assert type(env._sampler).__name__ == 'ConstantSampler' and type(env._init_sampler).__name__ == 'TriangleIntitializer'
+        smp = orc.PhiloxTemplateSampler(params, orc.triangle_template(params['init']), seed=seed)
+        env._init_sampler = smp
+        env.states, env.obstacles, env.target = smp()
+        init = dict(init_states=env.states.numpy().copy(), init_obstacles=env.obstacles.numpy().copy(),
+                    init_obs=fused(env.observations()))
+        T, B = 1000, 2
+        rec = dict(rewards=np.empty((T, B), np.float32), terminated=np.empty((T, B), bool),
+                   truncated=np.empty((T, B), bool), obs_sum=np.empty(T, np.uint64), states_sum=np.empty(T, np.uint64),
+                   obs_e0a0=np.empty((T, 12), np.float32), terminates=np.empty((T, B), bool),
+                   step_num=np.empty((T, B), np.float32), num_tar=np.empty(T, np.int64))
+        acts, snaps = [], {}
+        for t in range(T):
+            a = env.sample_actions()
+            acts.append(a.numpy().copy())
+            obs, rew, term, trunc = env.step(a)
+            o = fused(obs)
+            rec['rewards'][t], rec['terminated'][t], rec['truncated'][t] = rew.numpy(), term.numpy(), trunc.numpy()
+            rec['obs_sum'][t], rec['states_sum'][t], rec['obs_e0a0'][t] = checksum(o), checksum(env.states.numpy()), o[0, 0]
+            rec['terminates'][t], rec['step_num'][t], rec['num_tar'][t] = env._terminates.numpy(), env._step_num.numpy(), env._num_tar
+            if term.any() or t in (0, 1, 999):
+                snaps[f'states_{t}'] = env.states.numpy().copy(); snaps[f'obs_{t}'] = o
+                snaps[f'obstacles_{t}'] = env.obstacles.numpy().copy()
+        rec.update(snaps); rec.update(init)
+        rec['stats'] = np.array([env._num_trunc, env._num_col, env._num_tar], np.int64)
+        rec['actions'] = np.stack(acts)
+        rec['reward_sum_f64'] = np.array(rec['rewards'].astype(np.float64).sum())
+    save(name, dict(sn=-1, steps=T, seed=seed, B=B, A=3, O=3), rec)
+
+
+def models_case(name):
+    """The reference learner-side pieces SURVEY 8(f)-2/3 replace, run on fixed weights and inputs:
+    Actor.forward -> dist.sample() / dist.log_prob() (models.py:14-36,113-115; the standard-normal
+    draws of MultivariateNormal.rsample are injected through torch.distributions' own
+    `_standard_normal` hook, everything else is the reference's code path including its Cholesky),
+    Critic.forward (models.py:39-56) and MAPPO._process_rewards (models.py:131-148)."""
+    import types
+    import marlnav.models as models_mod
+    import torch.distributions.multivariate_normal as mvn
+    arrays = {}
+    for tag, (S, H, N, A) in dict(a=(12, 50, 4096, 3), b=(48, 64, 512, 8)).items():
+        torch.manual_seed(100 + S)
+        actor = models_mod.Actor(S, H)
+        critic = models_mod.Critic(A * S, H)
+        with torch.no_grad():                      # spread the heads so tanh / softplus see their whole range
+            actor.fc_mu.weight.mul_(1.7); actor.fc_std.weight.mul_(2.5); actor.fc_std.bias.add_(0.3)
+        g = torch.Generator().manual_seed(7 + S)
+        obs = (torch.rand(N // A, A, S, generator=g) * 2 - 1) * 1.2
+        eps = torch.randn(N // A * A, 2, generator=g)
+        saved = mvn._standard_normal
+        mvn._standard_normal = lambda shape, dtype, device: eps.reshape(shape).to(dtype)
+        try:
+            with torch.no_grad():
+                dist = actor(obs)
+                actions = dist.sample()
+                logp = dist.log_prob(actions)
+                values = critic(obs)
+        finally:
+            mvn._standard_normal = saved
+        arrays.update({f'{tag}_obs': obs.numpy(), f'{tag}_eps': eps.numpy(), f'{tag}_actions': actions.numpy(),
+                       f'{tag}_log_probs': logp.numpy(), f'{tag}_mu': dist.loc.numpy(),
+                       f'{tag}_var': torch.diagonal(dist.covariance_matrix, dim1=-2, dim2=-1).numpy().copy(),
+                       f'{tag}_values': values.numpy()})
+        for k, v in actor.state_dict().items(): arrays[f'{tag}_actor.{k}'] = v.numpy().copy()
+        for k, v in critic.state_dict().items(): arrays[f'{tag}_critic.{k}'] = v.numpy().copy()
+    # MAPPO._process_rewards on a fixed buffer, called unbound on a stand-in object (MAPPO.__init__
+    # creates directories and optimisers that have nothing to do with it)
+    T, B, gamma = 64, 37, 0.9
+    g = torch.Generator().manual_seed(5)
+    rewards = (torch.rand(T, B, generator=g) * 40 - 10)
+    done = torch.rand(T, B, generator=g) < 0.06
+    stub = types.SimpleNamespace(num_parallel=B, device='cpu', buffer_len=T, gamma=gamma, _mean_rew=0.,
+                                 _logs={'mean_rews': []},
+                                 buffer=[[None, None, None, None, rewards[i].clone(), done[i].clone()] for i in range(T)])
+    raw = []
+    orig_std_mean = torch.std_mean
+    def tap(x, *a, **k):                            # the discounted returns before normalisation
+        raw.append(x.clone()); return orig_std_mean(x, *a, **k)
+    torch.std_mean = tap
+    try:
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            models_mod.MAPPO._process_rewards(stub)
+    finally:
+        torch.std_mean = orig_std_mean
+    arrays.update(ret_rewards=rewards.numpy(), ret_done=done.numpy(), ret_gamma=np.array(gamma),
+                  ret_returns=raw[0].reshape(T, B).numpy(),
+                  ret_normalized=torch.stack([stub.buffer[i][-2] for i in range(T)]).numpy(),
+                  ret_mean=np.array(float(stub._mean_rew)))
+    save(name, dict(torch=torch.__version__), arrays)
+
+
 def quirk_case(name):
     """delayed target termination, collision+target,
     truncation -- 4 hand-placed envs, stock reference, constant action [0, -10]."""
@@ -178,6 +282,14 @@ def quirk_case(name):
 
 if __name__ == '__main__':
     assert refload.available(), "the reference must be mounted at /root/reference"
+    only = set(sys.argv[1:])                       # e.g. `make_golden.py snm1 models`: just those families
+    if only:
+        if 'snm1' in only:
+            snm1_case('patched_rc_snm1', 0, patched=True)
+            snm1_case('stock_rc_snm1', 0, patched=False)
+        if 'models' in only:
+            models_case('ref_models')
+        sys.exit(0)
     random_case('patched_tri_3x3', 48, 3, 3, 260, seed=7, act_seed=1234, patched=True)
     random_case('patched_tri_3x3_wide', 16, 3, 3, 60, seed=8, act_seed=99, patched=True, angle=4.0)
     random_case('patched_ring_8x16', 12, 8, 16, 80, seed=5, act_seed=4321, patched=True,
@@ -193,3 +305,6 @@ if __name__ == '__main__':
         scenario_case(f'patched_rc_sn{sn}', sn, patched=True)
         scenario_case(f'stock_rc_sn{sn}', sn, patched=False)
     quirk_case('patched_quirks')
+    snm1_case('patched_rc_snm1', 0, patched=True)
+    snm1_case('stock_rc_snm1', 0, patched=False)
+    models_case('ref_models')

@@ -44,26 +44,41 @@ def test_cuda_reproduces_termination_quirks():
     gr.replay_bit_exact("quirks", be, z, tag=" [cuda]")
 
 
-def test_cuda_vs_stock_reference_teacher_forced():
-    """Stock reference (MKL trig) per-step snapshots: flags / reset decisions bit-exact,
-    states and distances within 1e-5 (north-star tolerance)."""
-    import torch
+def test_cuda_reproduces_constant_sampler_scenario():
+    """BASELINE.json configs[0] as written: `python -m marlnav -rc -sn -1 -se 0` (triangle initialiser,
+    ConstantSampler [0, 1], B = 2, 1000 steps), reference-generated, bit for bit -- including the
+    target reaches this scenario alone produces in free running (stats[2] > 0)."""
     import marlnav_b200 as mb
-    meta, z = gr.load("stock_tri_3x3")
+    meta, z = gr.load("patched_rc_snm1")
+    be = gr.CudaBackend(mb, mb.default_env_params(sampler_num=-1), int(meta["seed"]))
+    for t in (0, 1, 2):      # the drop-in's ConstantSampler hands out the reference sampler's actions
+        assert np.array_equal(be.e.sample_actions().cpu().numpy(), z["actions"][t])
+    gr.replay_scenario("rc_snm1 [cuda]", be, z)
+    assert be.stats()[2] > 0 and be.stats()[1] > 0
+
+
+def test_cuda_vs_stock_constant_sampler_scenario():
+    """The same scenario against the STOCK reference (its own acos), free-running for 1000 steps:
+    every terminal flag, reset draw and episode counter identical, rewards within 1e-5."""
+    import marlnav_b200 as mb
+    meta, z = gr.load("stock_rc_snm1")
+    be = gr.CudaBackend(mb, mb.default_env_params(sampler_num=-1), int(meta["seed"]))
+    for t, act in enumerate(z["actions"]):
+        obs, rew, term, trunc = be.step(act)
+        assert np.array_equal(term, z["terminated"][t]) and np.array_equal(trunc, z["truncated"][t]), t
+        np.testing.assert_allclose(rew, z["rewards"][t], rtol=1e-5)
+        np.testing.assert_allclose(obs[0, 0], z["obs_e0a0"][t], rtol=1e-5, atol=1e-6)
+        if f"obstacles_{t}" in z.files:
+            assert np.array_equal(be.obstacles(), z[f"obstacles_{t}"])
+    assert be.stats() == tuple(int(v) for v in z["stats"])
+
+
+@pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16"])
+def test_cuda_vs_stock_reference_teacher_forced(name):
+    """Stock reference (MKL trig) per-step snapshots replayed on the GPU: flags / reset decisions
+    bit-exact; states, distances and rewards within 1e-5 (north-star tolerance); angles within 1e-5
+    up to acos conditioning; at most 2 heading-score flips on pi/8 straddles."""
+    meta, z = gr.load(name)
     be = _backend(meta)
-    e = be.e
-    O, A = e.num_obstacles, e.num_agents
-    snaps = {int(t): i for i, t in enumerate(z["snap_steps"])}
-    for k, t in enumerate(range(0, int(meta["steps"]), 4)):
-        e.states.copy_(torch.as_tensor(z["pre_states"][k])); e.obstacles.copy_(torch.as_tensor(z["pre_obstacles"][k]))
-        e.target.copy_(torch.as_tensor(z["pre_target"][k])); e._step_num.copy_(torch.as_tensor(z["pre_step_num"][k]))
-        e._terminates_u8.copy_(torch.as_tensor(z["pre_terminates"][k].astype(np.uint8)))
-        e._reset_counter = t
-        obs, rew, term, trunc = be.step(z["actions"][t])
-        i = snaps[t]
-        assert np.array_equal(term, z["terminated"][t]) and np.array_equal(trunc, z["truncated"][t])
-        assert np.array_equal(be.obstacles(), z["snap_obstacles"][i])        # same envs reset, same draws
-        assert np.array_equal(be.step_num(), z["snap_step_num"][i])
-        np.testing.assert_allclose(be.states(), z["snap_states"][i], rtol=1e-5, atol=1e-6)
-        dist_cols = [1] + list(range(2 + O, 2 + 2 * O)) + list(range(2 + 2 * O + A - 1, 2 + 2 * O + 2 * (A - 1)))
-        np.testing.assert_allclose(obs[:, :, dist_cols], z["snap_obs"][i][:, :, dist_cols], rtol=1e-5)
+    checked, flips = gr.teacher_forced_vs_stock(name + " [cuda]", be, z, meta, be.e.num_agents, be.e.num_obstacles)
+    assert checked >= 80 and flips <= 2

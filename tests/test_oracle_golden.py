@@ -95,51 +95,46 @@ def test_torch_port_reproduces_stock_reference(oracle, name):
         pytest.skip("host torch CPU trig differs from the golden-generating host; ran for crashes only")
 
 
-def _angle_tol(angle):
-    """Angles come from acos(dot): a heading that moved by 1 ulp moves dot by a few 6e-8, i.e. the
-    angle by that over sin(angle).  1e-5 relative wherever that conditioning allows it."""
-    return 1e-5 * np.abs(angle) + 5e-7 / np.maximum(np.abs(np.sin(angle)), 1e-3)
-
-
 @pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16"])
 def test_c_oracle_vs_stock_reference_teacher_forced(oracle, name):
     """Identical pre-step states and actions into the oracle and the STOCK reference (MKL trig):
     terminal flags and reset decisions bit-exact, states/distances/rewards within 1e-5,
-    angles within 1e-5 up to acos conditioning."""
+    angles within 1e-5 up to acos conditioning (golden_replay.teacher_forced_vs_stock)."""
     meta, z = gr.load(name)
     be = _oracle_backend(oracle, meta)
-    e = be.e
-    A, O = e.A, e.O
-    snaps = {int(t): i for i, t in enumerate(z["snap_steps"])}
-    checked = flips = 0
-    for k, t in enumerate(range(0, int(meta["steps"]), 4)):
-        e.states[...] = z["pre_states"][k]; e.obstacles[...] = z["pre_obstacles"][k]
-        e.target[...] = z["pre_target"][k].reshape(-1, 2); e.step_num[...] = z["pre_step_num"][k]
-        e.terminates[...] = z["pre_terminates"][k].astype(np.uint8)
-        e.counter = t                       # step t draws Philox counter t+1 in both
-        obs, rew, term, trunc, pre = e.step_fused(z["actions"][t], want_pre=True)
-        i = snaps[t]
-        assert_bits_equal(f"{name} step {t} truncated", trunc, z["truncated"][t])
-        assert_bits_equal(f"{name} step {t} terminated", term, z["terminated"][t])
-        assert_bits_equal(f"{name} step {t} obstacles", e.obstacles, z["snap_obstacles"][i])
-        assert_bits_equal(f"{name} step {t} step_num", e.step_num, z["snap_step_num"][i])
-        np.testing.assert_allclose(e.states, z["snap_states"][i], rtol=1e-5, atol=1e-6)
-        want = z["snap_obs"][i]
-        dist_cols = [1] + list(range(2 + O, 2 + 2 * O)) + list(range(2 + 2 * O + A - 1, 2 + 2 * O + 2 * (A - 1)))
-        ang_cols = [c for c in range(want.shape[2]) if c not in dist_cols]
-        np.testing.assert_allclose(obs[:, :, dist_cols], want[:, :, dist_cols], rtol=1e-5)
-        da = np.abs(obs[:, :, ang_cols] - want[:, :, ang_cols])
-        assert (da <= _angle_tol(want[:, :, ang_cols])).all(), f"{name} step {t}: angle beyond conditioning bound"
-        # rewards: 1e-5 unless a heading score (|target_angle| < pi/8, worth heading_factor/A) flipped
-        # on an angle that straddles the threshold within the trig difference
-        dr = np.abs(rew - z["rewards"][t])
-        bad = dr > 1e-5 * np.maximum(np.abs(z["rewards"][t]), 1.0)
-        if bad.any():
-            ta = np.abs(pre[bad][:, :, 0])
-            assert (np.abs(ta - np.float32(np.pi / 8)) < 1e-5).any(axis=1).all(), f"{name} step {t}: reward off"
-            flips += int(bad.sum())
-        checked += rew.size
+    checked, flips = gr.teacher_forced_vs_stock(name, be, z, meta, be.e.A, be.e.O)
     assert checked >= 80 and flips <= 2
+
+
+def test_c_oracle_reproduces_constant_sampler_scenario(oracle):
+    """BASELINE.json configs[0] as written: `python -m marlnav -rc -sn -1 -se 0` (triangle
+    initialiser + ConstantSampler, B = 2, 1000 steps; utils.py:217-243, 477-485).  The one
+    free-running scenario with target reaches (delayed termination, double-counted _num_tar)."""
+    import marlnav_b200 as mb
+    meta, z = gr.load("patched_rc_snm1")
+    p = mb.default_env_params(sampler_num=-1, device="cpu")
+    gr.replay_scenario("rc_snm1", gr.OracleBackend(oracle, p, int(meta["seed"])), z)
+    assert int(z["stats"][2]) > 0 and int(z["stats"][1]) > 0
+    # a reach is terminated one step late and counted on both steps (Appendix B-1)
+    reach = np.flatnonzero(np.diff(z["num_tar"], prepend=0))
+    assert len(reach) >= 2 and (np.diff(reach)[::2] == 1).all()
+
+
+def test_c_oracle_vs_stock_constant_sampler_scenario(oracle):
+    """The same scenario on the STOCK reference (its own acos): free-running for 1000 steps the
+    oracle keeps every terminal flag and reset draw and stays within 1e-5 on the rewards."""
+    import marlnav_b200 as mb
+    meta, z = gr.load("stock_rc_snm1")
+    be = gr.OracleBackend(oracle, mb.default_env_params(sampler_num=-1, device="cpu"), int(meta["seed"]))
+    for t, act in enumerate(z["actions"]):
+        obs, rew, term, trunc = be.step(act)
+        assert_bits_equal(f"step {t} terminated", term, z["terminated"][t])
+        assert_bits_equal(f"step {t} truncated", trunc, z["truncated"][t])
+        np.testing.assert_allclose(rew, z["rewards"][t], rtol=1e-5)
+        np.testing.assert_allclose(obs[0, 0], z["obs_e0a0"][t], rtol=1e-5, atol=1e-6)
+        if f"obstacles_{t}" in z.files:
+            assert_bits_equal(f"step {t} obstacles", be.obstacles(), z[f"obstacles_{t}"])
+    assert be.stats() == tuple(int(v) for v in z["stats"])
 
 
 def test_c_oracle_move_phase_vs_stock_reference(oracle):

@@ -68,7 +68,7 @@ def test_row_sum_matches_torch_sum(oracle, n):
 
 
 def test_trig_accuracy_sampled(oracle):
-    """marlnav_trig.h stays within the exhaustively measured bounds (1.38/1.48/1.12 ulp;
+    """marlnav_trig.h stays within the exhaustively measured bounds (1.38/1.48/2.10 ulp;
     oracle/verify_math.c sweeps every float32) on a dense sample incl. the edges."""
     rng = np.random.default_rng(0)
     t = np.concatenate([rng.uniform(-np.pi, np.pi, 2_000_000), [0.0, -0.0, np.pi, -np.pi, 1e-30, -1e-8]])
@@ -78,7 +78,7 @@ def test_trig_accuracy_sampled(oracle):
     assert _ulp_err(_trig(oracle, 1, t), np.cos(t.astype(np.float64))).max() < 1.50
     x = np.concatenate([rng.uniform(-1, 1, 2_000_000), 1 - np.logspace(-8, -1, 5000), [1.0, -1.0, 0.0, 0.5, -0.5]])
     x = x.astype(np.float32)
-    assert _ulp_err(_trig(oracle, 2, x), np.arccos(x.astype(np.float64))).max() < 1.13
+    assert _ulp_err(_trig(oracle, 2, x), np.arccos(x.astype(np.float64))).max() < 2.11
     assert _trig(oracle, 2, np.array([1.0], np.float32))[0] == 0.0
     s0 = _trig(oracle, 0, np.array([-0.0], np.float32))
     assert s0[0] == 0.0 and np.signbit(s0[0])          # sin(-0) = -0 like torch
@@ -86,8 +86,9 @@ def test_trig_accuracy_sampled(oracle):
 
 def test_trig_close_to_torch_cpu(oracle):
     """Against torch's own CPU sin/cos/acos (MKL VML or SLEEF, depending on the build) the
-    oracle trig differs by at most 2 ulp -- the same order as torch's backends differ from
-    each other -- which is what bounds the 1e-5 parity tolerance against the stock reference."""
+    oracle's sin/cos differ by at most 2 ulp -- the same order as torch's backends differ from
+    each other -- and its acos (2.10 ulp from exact) by at most 3: 3.6e-7 relative, against the 1e-5
+    parity tolerance versus the stock reference."""
     rng = np.random.default_rng(1)
     t = rng.uniform(-np.pi, np.pi, 1_000_000).astype(np.float32)
     x = rng.uniform(-1, 1, 1_000_000).astype(np.float32)
@@ -96,7 +97,7 @@ def test_trig_close_to_torch_cpu(oracle):
         got = _trig(oracle, which, arr)
         ulps = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
         big = np.abs(want) > 1e-3          # ulp distance is meaningless across a zero crossing
-        assert ulps[big].max() <= 2
+        assert ulps[big].max() <= (3 if which == 2 else 2)
 
 
 def test_sleef_restatement_known_bits(oracle):
