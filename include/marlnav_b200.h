@@ -24,7 +24,16 @@
  *       (environment.py:39), rewards (B), terminated/truncated (B) 1-byte bool.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *     All calls are asynchronous on that stream; none allocates or synchronises
- *     (the *_host variants enqueue copies; the caller synchronises).
+ *     (marlnav_step_host_f32 enqueues copies on the streams of a caller-owned
+ *     marlnav_host_pipe; the caller synchronises).
+ *   - Every struct passed by pointer starts with `struct_size` = its sizeof in the
+ *     caller's build (ABI 4); an entry that receives another size fails with
+ *     MARLNAV_ERR_BAD_ARG instead of reading past the caller's struct.
+ *   - Threading: the library keeps no mutable state between calls except caches of
+ *     idempotent facts (proven constant divisors, per-device kernel attributes; both
+ *     safe to race) and the calling thread's last-error string.  Calls on different
+ *     streams / devices may come from different threads; a marlnav_host_pipe must not
+ *     be used by two calls at a time.
  *   - Return value: 0 on success, a cudaError_t (>0) for a CUDA failure,
  *     <0 for an argument error; marlnav_last_error() describes the last failure
  *     of the calling thread.
@@ -40,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MARLNAV_ABI_VERSION 3
+#define MARLNAV_ABI_VERSION 4
 #define MARLNAV_MAX_AGENTS 26     /* torch.cdist's direct formula holds up to 25 columns */
 #define MARLNAV_MAX_OBSTACLES 64
 
@@ -52,6 +61,7 @@ extern "C" {
  * the geometry constants it hard-codes (environment.py:56-68) and the obstacle box
  * of TriangleIntitializer (utils.py:344-347).  Passed by pointer, read on the host. */
 typedef struct marlnav_env_params {
+    uint32_t struct_size;    /* sizeof(marlnav_env_params) */
     int32_t num_envs;        /* B = num_parallel (this process's slice) */
     int32_t num_agents;      /* A, 2..MARLNAV_MAX_AGENTS */
     int32_t num_obstacles;   /* O, 1..MARLNAV_MAX_OBSTACLES */
@@ -77,14 +87,24 @@ typedef struct marlnav_env_params {
 /* flags: no element of a SHARED tmpl_states (states_env_stride == 0) has its sign bit set,
  * so 0*template == +0 and the blend of a not-reset env reduces to old + 0 (no template reads) */
 #define MARLNAV_RESET_TMPL_NONNEG 1
+/* TriangleIntitializer with noisy_ags = True (utils.py:25, 381-388; shared template only): every
+ * (re-)initialised agent gets Gaussian position noise  pos += noise_mult * (noise_chol * z)  with
+ * z ~ N(0, I) (MultivariateNormal(0, diag(ags_std)).sample(): noise_chol = sqrt(ags_std),
+ * noise_mult = ags_dist) and its template heading rotated by angle_range * (u - 1/2).  The draws are
+ * Philox4x32-10 addressed by (seed; global env id, step_counter, 0x40000000 + agent): words 0-1
+ * -> Box-Muller normals, word 2 -> u.  Like the reference, which samples the whole batch every
+ * step and blends by mask, envs that do not reset evaluate the literal blend old + 0 * new. */
+#define MARLNAV_RESET_NOISY_AGENTS 2
 
 typedef struct marlnav_reset_spec {
+    uint32_t struct_size;      /* sizeof(marlnav_reset_spec) */
+    int32_t flags;             /* MARLNAV_RESET_* bits */
     const float* tmpl_states;
     const float* tmpl_obstacles;
     const float* tmpl_target;
     int64_t states_env_stride, obstacles_env_stride, target_env_stride;   /* in floats */
     int32_t alias_first_step;
-    int32_t flags;             /* MARLNAV_RESET_* bits */
+    float noise_chol, noise_mult, angle_range;   /* MARLNAV_RESET_NOISY_AGENTS only */
     uint64_t seed;
     uint64_t step_counter;     /* 0 at construction, k for the k-th step() call */
     uint64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */
@@ -101,6 +121,7 @@ typedef struct marlnav_reset_spec {
  *   ActionScaler   utils.py:535-547   action[k]   = scale[k] * raw[k] + mean[k]
  * All pointers device; NULL disables the corresponding transform. */
 typedef struct marlnav_io_transform {
+    uint64_t struct_size;      /* sizeof(marlnav_io_transform) */
     const float* obs_mean;     /* (S) */
     const float* obs_scale;    /* (S) */
     const float* act_mean;     /* (2) */
@@ -109,6 +130,12 @@ typedef struct marlnav_io_transform {
 
 int         marlnav_abi_version(void);
 const char* marlnav_last_error(void);
+/* sizeof of the structs in the library's build: a binding asserts they equal its own layouts. */
+size_t      marlnav_sizeof_env_params(void);
+size_t      marlnav_sizeof_reset_spec(void);
+size_t      marlnav_sizeof_io_transform(void);
+size_t      marlnav_sizeof_actor_spec(void);
+size_t      marlnav_sizeof_step_call(void);
 /* S = 2 + 2*O + 2*(A-1); 0 for invalid (A,O). */
 int         marlnav_obs_size(int num_agents, int num_obstacles);
 /* Number of CUDA devices visible (0 when there is none / no driver). */
@@ -146,13 +173,42 @@ int marlnav_step_f32(const marlnav_env_params* params, const marlnav_reset_spec*
                      unsigned long long* stats,
                      const marlnav_io_transform* io, void* stream);
 
+/* marlnav_step_f32 with its arguments in one caller-owned struct: a binding fills it once and
+ * changes only what differs between steps (actions, outputs, stream; the step counter lives in
+ * *reset).  Through Python's ctypes a 1-argument call costs ~2 us less than the 15-argument one,
+ * which is most of what a step of ~1000 envs costs on the host. */
+typedef struct marlnav_step_call {
+    uint64_t struct_size;      /* sizeof(marlnav_step_call) */
+    const marlnav_env_params* params;
+    const marlnav_reset_spec* reset;
+    float *states, *obstacles, *target, *step_num;
+    uint8_t* terminates;
+    const float* actions;
+    float *obs, *rewards;
+    uint8_t *terminated, *truncated;
+    unsigned long long* stats;
+    const marlnav_io_transform* io;
+    void* stream;
+} marlnav_step_call;
+int marlnav_step_call_f32(const marlnav_step_call* call);
+
+/* Streams and events of the host-stepping pipeline below, owned by the caller: created on the
+ * current device, used by one marlnav_step_host_f32 call at a time, destroyed by the caller.
+ * (The only entry points that allocate.) */
+typedef struct marlnav_host_pipe marlnav_host_pipe;
+int  marlnav_host_pipe_create(marlnav_host_pipe** pipe);
+void marlnav_host_pipe_destroy(marlnav_host_pipe* pipe);
+
 /* Same step for a HOST-resident policy: `actions_host` is copied H2D, the step
- * runs, and obs/rewards/flags are copied D2H, all enqueued on `stream`.  Host
+ * runs, and obs/rewards/flags are copied D2H; the batch is cut into chunks whose
+ * upload, step and download overlap on `stream` and the two streams of `pipe`;
+ * `stream` ends up waiting for the last download.  Host
  * buffers should be pinned for the copies to be asynchronous.  `actions_dev`,
  * `obs_dev`, `rewards_dev`, `terminated_dev`, `truncated_dev` are device staging
  * buffers of the usual shapes owned by the caller.  Environment state stays on
  * the device (it never leaves HBM between steps). */
-int marlnav_step_host_f32(const marlnav_env_params* params, const marlnav_reset_spec* reset,
+int marlnav_step_host_f32(marlnav_host_pipe* pipe,
+                          const marlnav_env_params* params, const marlnav_reset_spec* reset,
                           float* states, float* obstacles, float* target,
                           float* step_num, uint8_t* terminates,
                           const float* actions_host, float* actions_dev,
@@ -177,21 +233,25 @@ int marlnav_step_launch_info(const marlnav_env_params* params,
  *   actions = mu + sqrt(var)*eps;  log_probs = dist.log_prob(actions)
  * Weights are torch.nn.Linear layouts: w1 (H,S), b1 (H), w_mu/w_std (2,H), b_mu/b_std (2).
  * eps (N,2): standard-normal draws to use (parity tests) or NULL -> Philox4x32-10 + Box-Muller
- * addressed by (seed; row, counter); counter_dev, if non-NULL, is a DEVICE word added to `counter`
- * (ABI 3; CUDA-graph replays, same convention as marlnav_reset_spec.step_counter_dev).
- * mu_out/var_out (N,2) may be NULL. */
+ * addressed by (seed; row_offset + row, counter); counter_dev, if non-NULL, is a DEVICE word added to
+ * `counter` (CUDA-graph replays, same convention as marlnav_reset_spec.step_counter_dev).
+ * row_offset = the global index of local row 0 (env_id_offset * A for a sharded batch), so N ranks
+ * draw what one process would (ABI 4).  mu_out/var_out (N,2) may be NULL. */
 int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H,
                              const float* w1, const float* b1, const float* w_mu, const float* b_mu,
                              const float* w_std, const float* b_std,
                              const float* eps, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                             uint64_t row_offset,
                              float* actions, float* log_probs, float* mu_out, float* var_out, void* stream);
 
 /* The same actor as one struct, for the fused {actor -> step} launch. */
 typedef struct marlnav_actor_spec {
+    uint64_t struct_size;         /* sizeof(marlnav_actor_spec) */
     const float *w1, *b1, *w_mu, *b_mu, *w_std, *b_std;   /* device, torch.nn.Linear layouts as above */
     int32_t S, H;                 /* obs_size (must equal the env's), hidden (<= 256) */
     uint64_t seed, counter;       /* Philox addressing, as in marlnav_actor_sample_f32 */
     const uint64_t* counter_dev;  /* optional DEVICE word added to `counter` */
+    uint64_t row_offset;          /* global index of local row 0 (env_id_offset * A) */
 } marlnav_actor_spec;
 
 /* SURVEY.md section 8(f)-2, end state: MAPPO.get_data's inner iteration (models.py:113-122) as ONE

@@ -10,19 +10,30 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MARLNAV_B200_LIB may point at another build of the same ABI (A/B measurements only)
 LIB_PATH = os.environ.get("MARLNAV_B200_LIB") or os.path.join(_HERE, "libmarlnav_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/marlnav_b200.h declares
 EXPORTS = ("marlnav_abi_version", "marlnav_last_error", "marlnav_obs_size", "marlnav_device_count",
+           "marlnav_sizeof_env_params", "marlnav_sizeof_reset_spec", "marlnav_sizeof_io_transform",
+           "marlnav_sizeof_actor_spec", "marlnav_sizeof_step_call", "marlnav_step_call_f32",
+           "marlnav_host_pipe_create", "marlnav_host_pipe_destroy",
            "marlnav_counter_add", "marlnav_init_f32", "marlnav_observe_f32", "marlnav_step_f32", "marlnav_step_host_f32",
            "marlnav_step_launch_info", "marlnav_actor_sample_f32", "marlnav_act_step_f32", "marlnav_critic_value_f32",
            "marlnav_discounted_returns_f64",
            "marlnav_rollout_last_error")
 
 
-class EnvParams(ctypes.Structure):
+class _Sized(ctypes.Structure):
+    """Every ABI struct starts with ``struct_size`` = its sizeof (checked by the library)."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.struct_size = ctypes.sizeof(self)
+
+
+class EnvParams(_Sized):
     """struct marlnav_env_params"""
-    _fields_ = [(n, ctypes.c_int32) for n in
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in
                 ("num_envs", "num_agents", "num_obstacles", "episode_len")] + \
                [(n, ctypes.c_float) for n in (
                    "min_speed", "max_speed", "min_accel", "max_accel",
@@ -34,28 +45,43 @@ class EnvParams(ctypes.Structure):
                    "obst_x_range", "obst_x_mean", "obst_y_range", "obst_y_mean")]
 
 
-class ResetSpec(ctypes.Structure):
+RESET_TMPL_NONNEG, RESET_NOISY_AGENTS = 1, 2
+
+
+class ResetSpec(_Sized):
     """struct marlnav_reset_spec"""
-    _fields_ = [("tmpl_states", ctypes.c_void_p), ("tmpl_obstacles", ctypes.c_void_p),
+    _fields_ = [("struct_size", ctypes.c_uint32), ("flags", ctypes.c_int32),
+                ("tmpl_states", ctypes.c_void_p), ("tmpl_obstacles", ctypes.c_void_p),
                 ("tmpl_target", ctypes.c_void_p),
                 ("states_env_stride", ctypes.c_int64), ("obstacles_env_stride", ctypes.c_int64),
                 ("target_env_stride", ctypes.c_int64),
-                ("alias_first_step", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("alias_first_step", ctypes.c_int32), ("noise_chol", ctypes.c_float),
+                ("noise_mult", ctypes.c_float), ("angle_range", ctypes.c_float),
                 ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
                 ("env_id_offset", ctypes.c_uint64), ("step_counter_dev", ctypes.c_void_p)]
 
 
-class IoTransform(ctypes.Structure):
+class IoTransform(_Sized):
     """struct marlnav_io_transform"""
-    _fields_ = [("obs_mean", ctypes.c_void_p), ("obs_scale", ctypes.c_void_p),
+    _fields_ = [("struct_size", ctypes.c_uint64),
+                ("obs_mean", ctypes.c_void_p), ("obs_scale", ctypes.c_void_p),
                 ("act_mean", ctypes.c_void_p), ("act_scale", ctypes.c_void_p)]
 
 
-class ActorSpec(ctypes.Structure):
+class ActorSpec(_Sized):
     """struct marlnav_actor_spec"""
-    _fields_ = [(n, ctypes.c_void_p) for n in ("w1", "b1", "w_mu", "b_mu", "w_std", "b_std")] + \
+    _fields_ = [("struct_size", ctypes.c_uint64)] + \
+               [(n, ctypes.c_void_p) for n in ("w1", "b1", "w_mu", "b_mu", "w_std", "b_std")] + \
                [("S", ctypes.c_int32), ("H", ctypes.c_int32), ("seed", ctypes.c_uint64),
-                ("counter", ctypes.c_uint64), ("counter_dev", ctypes.c_void_p)]
+                ("counter", ctypes.c_uint64), ("counter_dev", ctypes.c_void_p), ("row_offset", ctypes.c_uint64)]
+
+
+class StepCall(_Sized):
+    """struct marlnav_step_call"""
+    _fields_ = [("struct_size", ctypes.c_uint64)] + \
+               [(n, ctypes.c_void_p) for n in ("params", "reset", "states", "obstacles", "target", "step_num",
+                                               "terminates", "actions", "obs", "rewards", "terminated", "truncated",
+                                               "stats", "io", "stream")]
 
 
 class MarlnavError(RuntimeError):
@@ -77,24 +103,38 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.marlnav_last_error.restype = ctypes.c_char_p
     lib.marlnav_rollout_last_error.restype = ctypes.c_char_p
+    sizeofs = ("marlnav_sizeof_env_params", "marlnav_sizeof_reset_spec", "marlnav_sizeof_io_transform",
+               "marlnav_sizeof_actor_spec", "marlnav_sizeof_step_call")
     for name in EXPORTS:
-        if name not in ("marlnav_last_error", "marlnav_rollout_last_error"):
+        if name in sizeofs:
+            getattr(lib, name).restype = ctypes.c_size_t
+        elif name == "marlnav_host_pipe_destroy":
+            lib.marlnav_host_pipe_destroy.restype = None
+        elif name not in ("marlnav_last_error", "marlnav_rollout_last_error"):
             getattr(lib, name).restype = ctypes.c_int
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     lib.marlnav_step_f32.argtypes = [vp] * 15
+    lib.marlnav_step_call_f32.argtypes = [vp]
     lib.marlnav_observe_f32.argtypes = [vp] * 6
     lib.marlnav_init_f32.argtypes = [vp] * 8
-    lib.marlnav_step_host_f32.argtypes = [vp] * 20
+    lib.marlnav_step_host_f32.argtypes = [vp] * 21
+    lib.marlnav_host_pipe_create.argtypes = [ctypes.POINTER(vp)]
+    lib.marlnav_host_pipe_destroy.argtypes = [vp]
     lib.marlnav_act_step_f32.argtypes = [vp] * 18
     lib.marlnav_obs_size.argtypes = [i32, i32]
     i64, u64, f64 = ctypes.c_longlong, ctypes.c_uint64, ctypes.c_double
-    lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64] + [vp] * 6
+    lib.marlnav_actor_sample_f32.argtypes = [vp, i64, i32, i32] + [vp] * 7 + [u64, u64, vp, u64] + [vp] * 5
     lib.marlnav_counter_add.argtypes = [vp, u64, vp]
     lib.marlnav_discounted_returns_f64.argtypes = [vp, vp, f64, i32, i64, vp, vp]
     lib.marlnav_critic_value_f32.argtypes = [vp, i64, i32, i32] + [vp] * 6
     got = lib.marlnav_abi_version()
     if got != ABI_VERSION:
         raise MarlnavError(f"libmarlnav_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild")
+    for cls, fn in ((EnvParams, lib.marlnav_sizeof_env_params), (ResetSpec, lib.marlnav_sizeof_reset_spec),
+                    (IoTransform, lib.marlnav_sizeof_io_transform), (ActorSpec, lib.marlnav_sizeof_actor_spec),
+                    (StepCall, lib.marlnav_sizeof_step_call)):
+        if ctypes.sizeof(cls) != fn():
+            raise MarlnavError(f"{cls.__name__}: binding layout is {ctypes.sizeof(cls)} bytes, the library's {fn()}")
     _lib = lib
     return lib
 

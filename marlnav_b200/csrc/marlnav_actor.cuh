@@ -9,7 +9,7 @@
 //   dist = MultivariateNormal(mu, covariance_matrix=diag(var))   -> std dev = sqrt(var)
 //   a = mu + sqrt(var) * eps;   log_prob(a), k = 2
 //
-// eps: given (parity tests), or Philox4x32-10 + Box-Muller addressed by (seed; row, counter).
+// eps: given (parity tests), or Philox4x32-10 + Box-Muller addressed by (seed; GLOBAL row, counter).
 // Weights in shared memory in torch.nn.Linear layout: w1 (H,S), b1 (H), w_mu/w_std (2,H).
 #pragma once
 #include <cuda_runtime.h>
@@ -57,7 +57,7 @@ template <int MAX_S>
 __device__ __forceinline__ ActorOut actor_row(const float (&x)[MAX_S], int S, int H, const ActorWeights& w,
                                               const float* __restrict__ b_mu, const float* __restrict__ b_std,
                                               const float* __restrict__ eps, uint64_t seed, uint64_t counter,
-                                              long long row) {
+                                              long long row, uint64_t grow /* global row: Philox address */) {
     float m0 = b_mu[0], m1 = b_mu[1], v0 = b_std[0], v1 = b_std[1];
     for (int j = 0; j < H; ++j) {
         float h = w.b1[j];
@@ -74,8 +74,9 @@ __device__ __forceinline__ ActorOut actor_row(const float (&x)[MAX_S], int S, in
     float e0, e1;
     if (eps) { e0 = eps[row * 2]; e1 = eps[row * 2 + 1]; }
     else {
-        const uint4 r = philox4x32_10((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)counter,
-                                      0x41435452u /* 'ACTR' */, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint4 r = philox4x32_10((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)counter,
+                                      0x41435452u /* 'ACTR' */, (uint32_t)seed,
+                                      (uint32_t)(seed >> 32) ^ (uint32_t)(counter >> 32));
         const float u1 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-08f;      // (0, 1]
         const float u2 = (float)(r.y >> 8) * 5.9604644775390625e-08f;               // [0, 1)
         const float rad = sqrtf(-2.0f * logf(u1));

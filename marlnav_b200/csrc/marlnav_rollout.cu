@@ -12,6 +12,7 @@
 // per-row Cholesky of MultivariateNormal around it, and the 1000-iteration Python loop after it.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -35,7 +36,7 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
                     const float* __restrict__ w_mu, const float* __restrict__ b_mu,
                     const float* __restrict__ w_std, const float* __restrict__ b_std,
                     const float* __restrict__ eps, uint64_t seed, uint64_t counter,
-                    const unsigned long long* __restrict__ counter_dev,
+                    const unsigned long long* __restrict__ counter_dev, uint64_t row_offset,
                     float* __restrict__ actions, float* __restrict__ log_probs,
                     float* __restrict__ mu_out, float* __restrict__ var_out) {
     extern __shared__ float sm[];
@@ -48,7 +49,8 @@ actor_sample_kernel(const float* __restrict__ obs, long long N, int S, int H,
 #pragma unroll
     for (int k = 0; k < MAX_S; ++k) x[k] = k < S ? obs[row * S + k] : 0.f;
     if (counter_dev) counter += __ldg(counter_dev);      // host value = offset inside a batch
-    const mna::ActorOut o = mna::actor_row<MAX_S>(x, S, H, mna::ActorWeights(sm, S, H), b_mu, b_std, eps, seed, counter, row);
+    const mna::ActorOut o = mna::actor_row<MAX_S>(x, S, H, mna::ActorWeights(sm, S, H), b_mu, b_std, eps, seed, counter, row,
+                                                      row_offset + (uint64_t)row);
     actions[row * 2] = o.a0; actions[row * 2 + 1] = o.a1;
     log_probs[row] = o.logp;
     if (mu_out) { mu_out[row * 2] = o.m0; mu_out[row * 2 + 1] = o.m1; }
@@ -204,6 +206,7 @@ const char* marlnav_rollout_last_error(void) { return g_err2; }
 int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H, const float* w1, const float* b1,
                              const float* w_mu, const float* b_mu, const float* w_std, const float* b_std,
                              const float* eps, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                             uint64_t row_offset,
                              float* actions, float* log_probs, float* mu_out, float* var_out, void* stream) {
     if (!obs || !w1 || !b1 || !w_mu || !b_mu || !w_std || !b_std || !actions || !log_probs || N < 1) {
         snprintf(g_err2, sizeof g_err2, "marlnav_actor_sample_f32: NULL pointer or empty batch");
@@ -217,25 +220,29 @@ int marlnav_actor_sample_f32(const float* obs, long long N, int S, int H, const 
     const long long grid = (N + threads - 1) / threads;
     const size_t smem = (size_t)(H * S + H + 4 * H) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    {   // same shared-memory carveout as the step kernels it alternates with (no SM reconfiguration)
-        static bool carve[64] = {false};
+    {   // same shared-memory carveout as the step kernels it alternates with (no SM reconfiguration),
+        // and room for the largest advertised shape (S = 64, H = 256: 69 KiB of weights)
+        static std::atomic<bool> carve[64];
         int dev0 = 0; cudaGetDevice(&dev0);
-        if (!carve[dev0 & 63]) {
+        if (!carve[dev0 & 63].load(std::memory_order_acquire)) {
+            const int max_smem = (256 * 64 + 5 * 256) * (int)sizeof(float);
             cudaFuncSetAttribute(mnr::actor_sample_kernel<16, 256>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(mnr::actor_sample_kernel<64, 256>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
-            carve[dev0 & 63] = true;
+            cudaFuncSetAttribute(mnr::actor_sample_kernel<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(mnr::actor_sample_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            carve[dev0 & 63].store(true, std::memory_order_release);
         }
     }
     if (S <= 16)
         mnr::actor_sample_kernel<16, 256><<<(unsigned)grid, threads, smem, st>>>(
             obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter,
-            reinterpret_cast<const unsigned long long*>(counter_dev), actions, log_probs, mu_out, var_out);
+            reinterpret_cast<const unsigned long long*>(counter_dev), row_offset, actions, log_probs, mu_out, var_out);
     else
         mnr::actor_sample_kernel<64, 256><<<(unsigned)grid, threads, smem, st>>>(
             obs, N, S, H, w1, b1, w_mu, b_mu, w_std, b_std, eps, seed, counter,
-            reinterpret_cast<const unsigned long long*>(counter_dev), actions, log_probs, mu_out, var_out);
+            reinterpret_cast<const unsigned long long*>(counter_dev), row_offset, actions, log_probs, mu_out, var_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err2, sizeof g_err2, "actor_sample launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
@@ -253,14 +260,14 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
     }
     if (B > 2048 && B <= 262144 && (size_t)(H * K + 32 * 64) * sizeof(float) <= 48 * 1024) {
         // mid-sized batches: 16 or 4 lanes per env (see critic_value_group_kernel)
-        static bool carve[64] = {false};
+        static std::atomic<bool> carve[64];
         int dev0 = 0; cudaGetDevice(&dev0);
-        if (!carve[dev0 & 63]) {
+        if (!carve[dev0 & 63].load(std::memory_order_acquire)) {
             cudaFuncSetAttribute(mnr::critic_value_group_kernel<16, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(mnr::critic_value_group_kernel<4, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
-            carve[dev0 & 63] = true;
+            carve[dev0 & 63].store(true, std::memory_order_release);
         }
         const bool l16 = B <= 32768;
         const int groups = l16 ? 8 : 32;
@@ -283,12 +290,12 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
         const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
         // same shared-memory carveout as the step kernels: SMs need not drain and reconfigure when
         // this runs beside them on a forked stream (collect_rollout)
-        static bool carve[64] = {false};
+        static std::atomic<bool> carve[64];
         int dev0 = 0; cudaGetDevice(&dev0);
-        if (!carve[dev0 & 63]) {
+        if (!carve[dev0 & 63].load(std::memory_order_acquire)) {
             cudaFuncSetAttribute(mnr::critic_value_wide_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
-            carve[dev0 & 63] = true;
+            carve[dev0 & 63].store(true, std::memory_order_release);
         }
         mnr::critic_value_wide_kernel<64><<<grid, 256, (size_t)(H * K + 4 * 64) * sizeof(float), (cudaStream_t)stream>>>(
             obs, B, K, H, w1, b1, w2, b2, values);
@@ -298,11 +305,11 @@ int marlnav_critic_value_f32(const float* obs, long long B, int K, int H, const 
     }
     const int threads = 128;
     const size_t smem = (size_t)H * K * sizeof(float);
-    static bool big_smem[64] = {false};
+    static std::atomic<bool> big_smem[64];
     int dev = 0; cudaGetDevice(&dev);
-    if (smem > 48 * 1024 && !big_smem[dev & 63]) {
+    if (smem > 48 * 1024 && !big_smem[dev & 63].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(mnr::critic_value_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        big_smem[dev & 63] = true;
+        big_smem[dev & 63].store(true, std::memory_order_release);
     }
     mnr::critic_value_kernel<64><<<(unsigned)((B + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(
         obs, B, K, H, w1, b1, w2, b2, values);

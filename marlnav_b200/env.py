@@ -31,13 +31,24 @@ Differences from the reference, all documented in DESIGN.md:
 """
 import ctypes
 import math
-from collections import namedtuple
+import sys
+from collections import deque, namedtuple
 
 import torch
 
 from . import _lib
 from .params import GEOMETRY
 from .samplers import action_sampler
+
+_storage_use_count = getattr(torch._C, '_storage_Use_Count', None)     # tensors sharing a storage
+
+
+
+def _refcounts(objs, _getref=sys.getrefcount):
+    """Reference counts of a slot's tensors; baseline and check go through this one function so
+    that the temporaries of the counting itself cancel."""
+    return [_getref(o) for o in objs]
+
 
 # Same type the reference returns (utils.py:13-15).
 Observations = namedtuple('Observations', ['target_angle', 'target_distance',
@@ -126,10 +137,12 @@ class Env(object):
         self._setup_reset_source(params['init'])
 
         B, A, O = self.num_parallel, self.num_agents, self.num_obstacles
+        self._ring = deque()              # reusable output slots of step() (see _take_slot)
+        self._ring_bytes = 0
         with torch.cuda.device(dev):
-            self.states = torch.empty(B, A, 5, device=dev)
-            self.obstacles = torch.empty(B, O, 2, device=dev)
-            self.target = torch.empty(B, 1, 2, device=dev)
+            self._states = torch.empty(B, A, 5, device=dev)
+            self._obstacles = torch.empty(B, O, 2, device=dev)
+            self._target = torch.empty(B, 1, 2, device=dev)
             self._step_num = torch.empty(B, device=dev)
             self._terminates_u8 = torch.empty(B, dtype=torch.uint8, device=dev)
             self._stats = torch.zeros(3, dtype=torch.int64, device=dev)   # trunc, col, tar
@@ -152,6 +165,28 @@ class Env(object):
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _raw_stream(self):
+        """cudaStream_t of torch's current stream on this device, as an int."""
+        try:
+            return torch._C._cuda_getCurrentRawStream(self.device.index)
+        except AttributeError:            # (private fast path; the public route costs ~1.5 us more)
+            return torch.cuda.current_stream(self.device).cuda_stream
+
+    # The reference rebinds env.states / env.obstacles / env.target on every step
+    # (environment.py:80-84) and callers may assign them; here they are updated in place, and an
+    # assignment re-binds the tensor the kernels work on (the cached launch arguments are rebuilt).
+    def _bind_state(self, name, value, shape):
+        t = torch.as_tensor(value, dtype=torch.float32, device=self.device).reshape(shape).contiguous()
+        setattr(self, name, t)
+        self.__dict__.pop('_call_cache', None)
+
+    states = property(lambda self: self._states,
+                      lambda self, v: self._bind_state('_states', v, (self.num_parallel, self.num_agents, 5)))
+    obstacles = property(lambda self: self._obstacles,
+                         lambda self, v: self._bind_state('_obstacles', v, (self.num_parallel, self.num_obstacles, 2)))
+    target = property(lambda self: self._target,
+                      lambda self, v: self._bind_state('_target', v, (self.num_parallel, 1, 2)))
 
     def _make_c_params(self):
         p = _lib.EnvParams()
@@ -178,10 +213,16 @@ class Env(object):
                 agents = _triangle_agents(init)
             else:
                 agents = torch.as_tensor(init['agent_template'], dtype=torch.float32).reshape(A, 5)
-            if init.get('noisy_ags'):
-                raise NotImplementedError("noisy_ags=True is hard-coded off in the reference "
-                                          "(utils.py:25) and not implemented here")
-            self._tmpl_nonneg = not bool(torch.signbit(agents).any())
+            # utils.py:25,381-388: Gaussian position noise + heading rotation on every (re-)initialised
+            # agent.  Constants with the reference's own float32 ops (utils.py:370-373: MultivariateNormal
+            # keeps scale_tril = cholesky(diag(ags_std, ags_std))).
+            self._noisy = bool(init.get('noisy_ags'))
+            if self._noisy:
+                chol = torch.linalg.cholesky(torch.diag(torch.tensor([init['ags_std'], init['ags_std']])))
+                self._noise = (float(chol[0, 0]), float(init['ags_dist']), float(init['angle_range']))
+            # (with noise the would-be sample of an env that does not reset can be negative, so the
+            # literal blend old + 0*new is evaluated instead of the "+0" shortcut)
+            self._tmpl_nonneg = not bool(torch.signbit(agents).any()) and not self._noisy
             self._tmpl_states = agents.to(dev).contiguous()
             self._tmpl_obstacles = None
             self._tmpl_target = torch.tensor([init['tar_pos_x'], init['tar_pos_y']], device=dev)
@@ -200,6 +241,7 @@ class Env(object):
                                              device=dev).reshape(B, 2).contiguous()
             self._per_env_template = True
             self._tmpl_nonneg = False
+            self._noisy = False
         else:
             raise ValueError(f"unknown init_method {method!r}")
 
@@ -213,7 +255,10 @@ class Env(object):
         rs.obstacles_env_stride = self.num_obstacles * 2 if per_env else 0
         rs.target_env_stride = 2 if per_env else 0
         rs.alias_first_step = 1 if alias else 0
-        rs.flags = 1 if (not per_env and self._tmpl_nonneg) else 0      # MARLNAV_RESET_TMPL_NONNEG
+        rs.flags = _lib.RESET_TMPL_NONNEG if (not per_env and self._tmpl_nonneg) else 0
+        if self._noisy:
+            rs.flags |= _lib.RESET_NOISY_AGENTS
+            rs.noise_chol, rs.noise_mult, rs.angle_range = self._noise
         rs.seed, rs.env_id_offset = self._seed, self._env_id_offset
         # ABI 3: the kernels use step_counter + *step_counter_dev
         rs.step_counter = self._reset_counter if self._counter_dev is None else self._counter_pending
@@ -271,6 +316,7 @@ class Env(object):
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             sp = actor.spec(actor._advance_counter(stream))
+            sp.row_offset = self._env_id_offset * self.num_agents if actor.row_offset is None else actor.row_offset
             self._reset_counter += 1
             rs = self._reset_spec(alias=self._alias_pending)
             rs.step_counter = self._advance_device_counter()
@@ -349,6 +395,7 @@ class Env(object):
             io.act_mean, io.act_scale = mean.data_ptr(), scale.data_ptr()
             keep += [mean, scale]
         self._io, self._io_tensors = (io, keep) if keep else (None, None)
+        self.__dict__.pop('_call_cache', None)
 
     def observations_fused(self):
         """(B,A,S) observation buffer of the current states (one kernel launch)."""
@@ -376,54 +423,141 @@ class Env(object):
         trunc = buf[n_obs + n_rew + n_flag:n_obs + n_rew + n_flag + B]
         return obs, rew, term, trunc
 
+    # ---- output slots.  step() must hand out FRESH tensors (the reference's rollout buffer keeps a
+    # reference to every step's rewards, models.py:121), but allocating them and cutting the six
+    # Observations views costs more host time than the launch at small batches.  A slot = one
+    # buffer with all its views prebuilt; a slot is handed out again only when nobody outside holds
+    # any of its tensors: every Python object of the slot is back at its resting reference count
+    # AND the buffer's storage is shared by no tensor beyond the slot's own (a caller's slice of a
+    # slice is a new tensor on the same storage).  Busy slots are skipped and a new one is made, so
+    # a caller that keeps T steps simply grows the ring to T slots (capped; past the cap, or on a
+    # torch without the storage use-count hook, plain allocation every step).
+    _RING_MAX_SLOTS = 4096
+    _RING_MAX_BYTES = 2 << 30
+
+    def _new_slot(self):
+        obs, rew, term, trunc = self._alloc_outputs()
+        fields = split_observations(obs, self.num_agents, self.num_obstacles)
+        tb, cb = term.view(torch.bool), trunc.view(torch.bool)
+        storage = obs.untyped_storage()
+        objs = (obs, rew, tb, cb, fields) + tuple(fields)
+        slot = dict(obs=obs, rew=rew, term=tb, trunc=cb, fields=fields, storage=storage, objs=objs,
+                    ptrs=(obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr()),
+                    nbytes=storage.nbytes(), u8=(term, trunc), call=_lib.StepCall(), epoch=0)
+        del obs, rew, term, trunc, fields, tb, cb
+        slot['rest'] = _refcounts(objs)
+        slot['shared'] = _storage_use_count(storage._cdata) if _storage_use_count else -1
+        return slot
+
+    def _slot_free(self, slot):
+        if not _storage_use_count or _storage_use_count(slot['storage']._cdata) != slot['shared']:
+            return False
+        return _refcounts(slot['objs']) == slot['rest']
+
+    def _take_slot(self):
+        ring = self._ring
+        for _ in range(min(len(ring), 3)):        # (a few tries: a caller may be holding some slots for long)
+            slot = ring[0]
+            ring.rotate(-1)
+            if self._slot_free(slot):
+                return slot
+        slot = self._new_slot()
+        if len(ring) < self._RING_MAX_SLOTS and self._ring_bytes + slot['nbytes'] <= self._RING_MAX_BYTES:
+            ring.append(slot)
+            self._ring_bytes += slot['nbytes']
+        return slot
+
     def _step_call_cache(self):
-        """ctypes argument objects that never change between steps (state tensors are updated in
-        place, so their pointers are stable): built once, the per-step host cost is what bounds
-        small batches."""
+        """Launch arguments that do not change between steps (state tensors are updated in place;
+        assigning env.states / .obstacles / .target, fuse_io, use_device_counter and the aliasing
+        hand-over drop this cache): built once, because the per-step host cost is what bounds small
+        batches.  `epoch` tells a slot's prebuilt marlnav_step_call that it is stale."""
         c = self.__dict__.get('_call_cache')
         if c is None:
             rs = self._reset_spec(alias=False)
-            c = dict(rs=rs, rs_ref=ctypes.byref(rs), p_ref=ctypes.byref(self._c_params),
-                     fixed=(self._ptr(self.states), self._ptr(self.obstacles), self._ptr(self.target),
-                            self._ptr(self._step_num), self._ptr(self._terminates_u8)),
-                     stats=self._ptr(self._stats), fn=self._lib.marlnav_step_f32)
+            self._call_epoch = self.__dict__.get('_call_epoch', 0) + 1
+            c = dict(rs=rs, epoch=self._call_epoch, fn=self._lib.marlnav_step_call_f32)
             self._call_cache = c
         return c
+
+    def _fill_call(self, call, c, ptrs):
+        """A marlnav_step_call for this env writing to the output pointers `ptrs`."""
+        call.params = ctypes.addressof(self._c_params)
+        call.reset = ctypes.addressof(c['rs'])
+        call.states, call.obstacles, call.target = self._states.data_ptr(), self._obstacles.data_ptr(), self._target.data_ptr()
+        call.step_num, call.terminates = self._step_num.data_ptr(), self._terminates_u8.data_ptr()
+        call.obs, call.rewards, call.terminated, call.truncated = ptrs
+        call.stats = self._stats.data_ptr()
+        call.io = ctypes.addressof(self._io) if self._io is not None else None
+        return call
+
+    def _launch_step(self, actions, ptrs, slot=None):
+        """One fused step launch writing to the four output pointers `ptrs` (or to `slot`'s)."""
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.numel() != self.num_parallel * self.num_agents * 2:
+            raise _lib.MarlnavError(f"actions must be ({self.num_parallel},{self.num_agents},2), got {tuple(actions.shape)}")
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self._launch_step(actions, ptrs, slot)
+        c = self._step_call_cache()
+        if slot is not None:
+            call = slot['call']
+            if slot['epoch'] != c['epoch']:
+                self._fill_call(call, c, slot['ptrs'])
+                slot['epoch'] = c['epoch']
+        else:
+            # caller-supplied outputs: their calls are remembered too (rollout buffers, CUDA-graph capture)
+            calls = c.setdefault('out_calls', {})
+            call = calls.get(ptrs)
+            if call is None:
+                if len(calls) >= 256:
+                    calls.clear()
+                call = calls[ptrs] = self._fill_call(_lib.StepCall(), c, ptrs)
+        rs = c['rs']
+        # the counters move only once the launch has been accepted
+        counter_dev, batch = self._counter_dev, self._counter_batch
+        stream = self._raw_stream()
+        if counter_dev is None:
+            rs.step_counter = self._reset_counter + 1
+        elif batch:
+            rs.step_counter = self._counter_pending + 1
+        else:
+            self._lib.marlnav_counter_add(counter_dev.data_ptr(), 1, stream)
+            rs.step_counter = 0
+        if self._alias_pending:
+            rs.alias_first_step = 1
+        call.actions = actions.data_ptr()
+        call.stream = stream
+        rc = c['fn'](ctypes.addressof(call))
+        if rc:
+            _lib.check(rc, "marlnav_step_call_f32")
+        self._reset_counter += 1
+        if batch and counter_dev is not None:
+            self._counter_pending += 1
+        if self._alias_pending:
+            # the reference's template froze at "state after the first move" (B-6)
+            self._tmpl_states = self._states.clone()
+            self._alias_pending = False
+            self.__dict__.pop('_call_cache', None)      # template pointer changed
 
     def step_fused(self, actions, out=None):
         """One fused step.  Returns ``(obs (B,A,S), rewards (B), terminated (B) bool,
         truncated (B) bool)``; ``out`` may supply preallocated (obs, rewards,
         terminated_u8, truncated_u8) tensors to write into."""
-        B, A = self.num_parallel, self.num_agents
-        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
-            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
-        if actions.numel() != B * A * 2:
-            raise _lib.MarlnavError(f"actions must be ({B},{A},2), got {tuple(actions.shape)}")
-        with torch.cuda.device(self.device):
-            obs, rew, term, trunc = out if out is not None else self._alloc_outputs()
-            self._reset_counter += 1
-            c = self._step_call_cache()
-            rs = c['rs']
-            rs.step_counter = self._advance_device_counter()
-            if self._alias_pending:
-                rs.alias_first_step = 1
-            rc = c['fn'](c['p_ref'], c['rs_ref'], *c['fixed'], actions.data_ptr(),
-                         obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), c['stats'],
-                         ctypes.byref(self._io) if self._io is not None else None,
-                         torch.cuda.current_stream(self.device).cuda_stream)
-            if rc:
-                _lib.check(rc, "marlnav_step_f32")
-            if self._alias_pending:
-                # the reference's template froze at "state after the first move" (B-6)
-                self._tmpl_states = self.states.clone()
-                self._alias_pending = False
-                self.__dict__.pop('_call_cache', None)      # template pointer changed
-        return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
+        if out is not None:
+            obs, rew, term, trunc = out
+            self._launch_step(actions, (obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr()))
+            return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
+        slot = self._take_slot()
+        self._launch_step(actions, None, slot)
+        return slot['obs'], slot['rew'], slot['term'], slot['trunc']
 
     def step(self, actions):
         """environment.py:92-107"""
-        obs, rew, term, trunc = self.step_fused(actions)
-        return split_observations(obs, self.num_agents, self.num_obstacles), rew, term, trunc
+        slot = self._take_slot()
+        self._launch_step(actions, None, slot)
+        return slot['fields'], slot['rew'], slot['term'], slot['trunc']
 
     def launch_info(self):
         """(grid, block, dynamic smem bytes, envs per CTA) of the step kernel for this shape."""
@@ -455,6 +589,22 @@ class HostStepper:
         self.truncated_dev = torch.empty(B, dtype=torch.uint8, device=dev)
         self.h2d_bytes = self.actions_host.numel() * 4
         self.d2h_bytes = self.obs_host.numel() * 4 + B * 4 + 2 * B
+        # the pipeline's two side streams and events belong to this stepper (marlnav_host_pipe)
+        self._pipe = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(env._lib.marlnav_host_pipe_create(ctypes.byref(self._pipe)), "marlnav_host_pipe_create")
+
+    def close(self):
+        pipe, self._pipe = getattr(self, '_pipe', None), None
+        if pipe:
+            torch.cuda.synchronize(self.env.device)
+            self.env._lib.marlnav_host_pipe_destroy(pipe)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def step(self, actions=None, sync=True):
         """Consumes ``actions`` (a pinned CPU float32 tensor of shape (B,A,2); default
@@ -471,7 +621,7 @@ class HostStepper:
             rs = env._reset_spec(alias=env._alias_pending)
             rs.step_counter = step_counter
             _lib.check(env._lib.marlnav_step_host_f32(
-                ctypes.byref(env._c_params), ctypes.byref(rs),
+                self._pipe, ctypes.byref(env._c_params), ctypes.byref(rs),
                 p(env.states), p(env.obstacles), p(env.target), p(env._step_num), p(env._terminates_u8),
                 p(src), p(self.actions_dev), p(self.obs_dev), p(self.rewards_dev),
                 p(self.terminated_dev), p(self.truncated_dev),

@@ -30,8 +30,12 @@ class FusedActor:
     """Inference-side twin of the reference ``Actor`` (models.py:14-36): takes its weights
     (``fc1``, ``fc_mu``, ``fc_std``) and samples actions + log-probs in one launch."""
 
-    def __init__(self, actor, device='cuda', seed=None):
+    def __init__(self, actor, device='cuda', seed=None, row_offset=None):
+        """``row_offset``: global index of this process's first (env, agent) row -- the sampling noise
+        is addressed by GLOBAL row, so N ranks stepping N slices draw what one process would.  Left
+        at None, ``collect_rollout`` / ``Env.act_step_fused`` use the env's ``env_id_offset * A``."""
         self._lib = _lib.load()
+        self.row_offset = row_offset
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.MarlnavError("FusedActor needs a CUDA device (no CPU fallback)")
@@ -89,6 +93,7 @@ class FusedActor:
         sp.w_std, sp.b_std = self.w_std.data_ptr(), self.b_std.data_ptr()
         sp.S, sp.H, sp.seed, sp.counter = self.obs_size, self.hidden, self.seed, counter
         sp.counter_dev = self._counter_dev.data_ptr() if self._counter_dev is not None else None
+        sp.row_offset = int(self.row_offset or 0)
         return sp
 
     def batch_device_counter(self, enable=True):
@@ -103,11 +108,14 @@ class FusedActor:
                                           torch.cuda.current_stream(self.device).cuda_stream)
         self._counter_pending = 0
 
-    def act(self, obs, eps=None, want_moments=False, out=None):
+    def act(self, obs, eps=None, want_moments=False, out=None, row_offset=None):
         """``obs``: normalised observations (..., obs_size) on the device (e.g. the fused (B,A,S)
         buffer).  Returns ``(actions (N,2), log_probs (N,))`` with N = prod(leading dims), exactly
         what models.py:113-115 produces; ``eps`` (N,2) injects the normal draws (tests); ``out`` =
-        preallocated contiguous ``(actions, log_probs)`` tensors to write into."""
+        preallocated contiguous ``(actions, log_probs)`` tensors to write into; ``row_offset``
+        overrides ``self.row_offset`` for this call."""
+        if row_offset is None:
+            row_offset = self.row_offset or 0
         x = obs.reshape(-1, self.obs_size)
         if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
             x = x.to(device=self.device, dtype=torch.float32).contiguous()
@@ -127,7 +135,7 @@ class FusedActor:
             counter = self._advance_counter(stream)
             _rollout_check(self._lib.marlnav_actor_sample_f32(
                 p(x), n, self.obs_size, self.hidden, p(self.w1), p(self.b1), p(self.w_mu), p(self.b_mu),
-                p(self.w_std), p(self.b_std), p(eps), self.seed, counter, p(self._counter_dev),
+                p(self.w_std), p(self.b_std), p(eps), self.seed, counter, p(self._counter_dev), int(row_offset),
                 p(actions), p(log_probs), p(mu), p(var), stream), "marlnav_actor_sample_f32")
         return (actions, log_probs, mu, var) if want_moments else (actions, log_probs)
 
@@ -257,7 +265,8 @@ def collect_rollout(env, actor, buffer_len, critic=None, normalizer_params=None,
                 env.act_step_fused(actor, obs, out=(buf['actions'][t], buf['log_probs'][t], obs_all[t + 1],
                                                     buf['rewards'][t], term[t], trunc[t]))
                 continue
-            actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]))   # models.py:113-115
+            actions, _ = actor.act(obs, out=(buf['actions'][t], buf['log_probs'][t]),     # models.py:113-115
+                                   row_offset=actor.row_offset if actor.row_offset is not None else env._env_id_offset * A)
             # raw [-1,1] actions in, normalised next observations out (models.py:116-118,122)
             env.step_fused(actions.view(B, A, 2), out=(obs_all[t + 1], buf['rewards'][t], term[t], trunc[t]))
     finally:

@@ -68,6 +68,12 @@ typedef struct {
     int32_t alias_first_step;     /* MockInitializer aliasing quirk, SURVEY Appendix B-6 */
     int32_t flags;
     uint64_t seed, step_counter, env_id_offset;
+    /* TriangleIntitializer with noisy_ags = True (utils.py:25, 381-388): Gaussian position noise
+     * and a random heading rotation on top of the agent template; 0 = off */
+    int32_t noisy;
+    float noise_chol;             /* cholesky(diag(ags_std, ags_std))[0][0] = sqrt(ags_std), utils.py:370-373 */
+    float noise_mult;             /* ags_dist, utils.py:382 */
+    float angle_range;            /* utils.py:383 */
 } mo_reset;
 
 /* ---------------------------------------------------------------- Philox */
@@ -101,7 +107,8 @@ static void mo_sample_obstacles(const mo_params* p, uint64_t seed, uint64_t step
     for (int pair = 0; 2 * pair < O; ++pair) {
         uint32_t r[4];
         mo_philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step_counter,
-                         (uint32_t)pair, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                         (uint32_t)pair, (uint32_t)seed,
+                         (uint32_t)(seed >> 32) ^ (uint32_t)(step_counter >> 32), r);
         for (int h = 0; h < 2; ++h) {
             int j = 2 * pair + h;
             if (j >= O) break;
@@ -113,6 +120,60 @@ static void mo_sample_obstacles(const mo_params* p, uint64_t seed, uint64_t step
         }
     }
 }
+
+/* The three draws of agent `agent` of one env for one (seed, step_counter): two standard normals
+ * (Box-Muller) and one uniform, Philox-addressed like the obstacles (counter word 3 =
+ * 0x40000000 + agent, disjoint from the obstacle pairs' 0..31). */
+static void mo_agent_draw(uint64_t seed, uint64_t step_counter, uint64_t env_id, int agent,
+                          float* z0, float* z1, float* u) {
+    uint32_t r[4];
+    mo_philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step_counter,
+                     0x40000000u + (uint32_t)agent, (uint32_t)seed,
+                     (uint32_t)(seed >> 32) ^ (uint32_t)(step_counter >> 32), r);
+    const float u1 = ((float)(r[0] >> 8) + 1.0f) * 5.9604644775390625e-08f;     /* (0, 1] */
+    mt_box_muller(u1, mo_u01(r[1]), z0, z1);
+    *u = mo_u01(r[2]);
+}
+
+/* utils.py:381-388 for one env, noisy_ags = 1:
+ *   pos_noise = ags_dist * (scale_tril @ eps)          :382  (MultivariateNormal.sample = loc + L eps)
+ *   angles    = angle_range * (rand - 0.5)             :383
+ *   dirs      = [[c,-s],[s,c]] @ dir                   :384, 400-408  (unfused, like environment.py:131-137)
+ *   positions = ags_pos + pos_noise                    :385 */
+static void mo_sample_agents_noisy(const mo_reset* rs, uint64_t step_counter, uint64_t env_id, int A,
+                                   const float* tmpl /* (A,5) */, float* out /* (A,5) */) {
+    for (int i = 0; i < A; ++i) {
+        float z0, z1, u;
+        mo_agent_draw(rs->seed, step_counter, env_id, i, &z0, &z1, &u);
+        const float ang = rs->angle_range * (u - 0.5f);
+        float sn, cs;
+        mt_sincosf(ang, &sn, &cs);
+        const float* t = tmpl + 5 * i;
+        out[5 * i + 0] = t[0] + (rs->noise_mult * (rs->noise_chol * z0));
+        out[5 * i + 1] = t[1] + (rs->noise_mult * (rs->noise_chol * z1));
+        out[5 * i + 2] = (cs * t[2]) + ((-sn) * t[3]);
+        out[5 * i + 3] = (sn * t[2]) + (cs * t[3]);
+        out[5 * i + 4] = t[4];
+    }
+}
+
+/* whole batch: the sampler's agent states (init, and golden injection into the reference) */
+void mo_noisy_agents(const mo_reset* rs, uint64_t step_counter, int64_t B, int A, float* out /* (B,A,5) */) {
+    for (int64_t b = 0; b < B; ++b)
+        mo_sample_agents_noisy(rs, step_counter, rs->env_id_offset + (uint64_t)b, A,
+                               rs->tmpl_states + (size_t)b * rs->states_env_stride, out + (size_t)b * A * 5);
+}
+/* the raw draws (normals (B,A,2), uniforms (B,A)) -- injected into the REAL reference's
+ * TriangleIntitializer when the noisy goldens are generated (tests/golden/make_golden.py) */
+void mo_agent_draws(uint64_t seed, uint64_t step_counter, uint64_t env_id_offset, int64_t B, int A,
+                    float* normals, float* uniforms) {
+    for (int64_t b = 0; b < B; ++b)
+        for (int i = 0; i < A; ++i)
+            mo_agent_draw(seed, step_counter, env_id_offset + (uint64_t)b, i,
+                          normals + ((size_t)b * A + i) * 2, normals + ((size_t)b * A + i) * 2 + 1,
+                          uniforms + (size_t)b * A + i);
+}
+void mo_log01(const float* x, float* y, size_t n) { for (size_t i = 0; i < n; ++i) y[i] = mt_logf01(x[i]); }
 
 void mo_philox_obstacles(const mo_params* p, uint64_t seed, uint64_t step_counter,
                          uint64_t env_id_offset, float* obstacles /* (B,O,2) */) {
@@ -354,6 +415,11 @@ void mo_step(const mo_params* p, const mo_reset* rs, float* states, float* obsta
                 mo_sample_obstacles(p, rs->seed, rs->step_counter, rs->env_id_offset + (uint64_t)b, newob);
                 to = newob;
             }
+            float noisy[5 * MO_MAX_AGENTS];
+            if (rs->noisy) {     /* the reference samples the whole batch every step and blends by mask */
+                mo_sample_agents_noisy(rs, rs->step_counter, rs->env_id_offset + (uint64_t)b, A, ts, noisy);
+                ts = noisy;
+            }
             for (int k = 0; k < A * 5; ++k) st[k] = mo_blend(st[k], ts[k], m);
             for (int k = 0; k < O * 2; ++k) ob[k] = mo_blend(ob[k], to[k], m);
             for (int k = 0; k < 2; ++k) tg[k] = mo_blend(tg[k], tt[k], m);
@@ -396,4 +462,4 @@ void mo_trig_sleef(int which, const float* x, float* y, size_t n) {
         y[i] = which == 0 ? tcm_sinf(x[i]) : which == 1 ? tcm_cosf(x[i]) : tcm_acosf(x[i]);
 }
 
-int mo_abi_version(void) { return 1; }
+int mo_abi_version(void) { return 2; }

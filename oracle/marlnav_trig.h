@@ -35,6 +35,8 @@
 #define MARLNAV_ORACLE_TRIG_H
 
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
 
 #define MT_2_PI    0.636619746685028076171875f      /* RN(2/pi) */
 #define MT_PIO2_HI 1.57079637050628662109375f       /* RN(pi/2) */
@@ -82,6 +84,47 @@ static inline float mt_acosf(float x) {
     p = fmaf(p, a, MT_ACOS_C0);
     const float r = t * p;                           /* acos(|x|) */
     return x < 0.0f ? (MT_PI_HI - (r - MT_PI_LO)) : r;
+}
+
+/* ln(x) for x in [2^-24, 1] -- the Box-Muller radius of the noisy agent reset
+ * (/root/reference/marlnav/utils.py:381-385 draws its position noise from
+ * MultivariateNormal, i.e. torch.randn on the CPU generator; here the normals are
+ * addressed Philox draws, SURVEY.md Appendix D, so they need a logarithm both sides
+ * can reproduce).  Cephes-style logf: x = m 2^e with m in [sqrt(1/2), sqrt(2)),
+ * f = m - 1, ln(1+f) = f - f^2/2 + f^3 P(f), e ln2 split in two.  IEEE-only
+ * (integer exponent extraction, + - * fma).  Max error 0.83 ulp over all 2^24
+ * inputs k 2^-24 the sampler can produce (oracle/verify_math.c). */
+static inline float mt_logf01(float x) {
+    uint32_t b; memcpy(&b, &x, 4);
+    int e = (int)((b >> 23) & 0xffu) - 126;          /* x = m 2^e, m in [1/2, 1) */
+    b = (b & 0x007fffffu) | 0x3f000000u;
+    float m; memcpy(&m, &b, 4);
+    float f;
+    if (m < 0.707106781186547524f) { e -= 1; f = (m + m) - 1.0f; } else { f = m - 1.0f; }
+    const float z = f * f;
+    float p = 7.0376836292e-2f;
+    p = fmaf(p, f, -1.1514610310e-1f);
+    p = fmaf(p, f, 1.1676998740e-1f);
+    p = fmaf(p, f, -1.2420140846e-1f);
+    p = fmaf(p, f, 1.4249322787e-1f);
+    p = fmaf(p, f, -1.6668057665e-1f);
+    p = fmaf(p, f, 2.0000714765e-1f);
+    p = fmaf(p, f, -2.4999993993e-1f);
+    p = fmaf(p, f, 3.3333331174e-1f);
+    const float fe = (float)e;
+    float y = (f * z) * p;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z, -0.5f, y);
+    return fmaf(fe, 0.693359375f, f + y);
+}
+
+/* Two independent standard normals from two uniforms, u1 in (0, 1], u2 in [0, 1):
+ * r = sqrt(-2 ln u1), theta = 2 pi (u2 - 1/2) in [-pi, pi). */
+static inline void mt_box_muller(float u1, float u2, float* z0, float* z1) {
+    const float rad = sqrtf(-2.0f * mt_logf01(u1));
+    float sn, cs;
+    mt_sincosf(6.2831854820251465f * (u2 - 0.5f), &sn, &cs);
+    *z0 = rad * cs; *z1 = rad * sn;
 }
 
 #endif

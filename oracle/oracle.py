@@ -66,7 +66,9 @@ class MoReset(ctypes.Structure):
                 ("target_env_stride", ctypes.c_int64),
                 ("alias_first_step", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("seed", ctypes.c_uint64), ("step_counter", ctypes.c_uint64),
-                ("env_id_offset", ctypes.c_uint64)]
+                ("env_id_offset", ctypes.c_uint64),
+                ("noisy", ctypes.c_int32), ("noise_chol", ctypes.c_float),
+                ("noise_mult", ctypes.c_float), ("angle_range", ctypes.c_float)]
 
 
 def build(force: bool = False) -> str:
@@ -181,7 +183,7 @@ def philox_obstacles_numpy(params: MoParams, seed, step_counter, env_id_offset=0
     c1 = np.repeat((env >> np.uint64(32)), npair)
     c2 = np.full(B * npair, step_counter & 0xFFFFFFFF, np.uint64)
     c3 = np.tile(np.arange(npair, dtype=np.uint64), B)
-    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64(((seed >> 32) ^ (step_counter >> 32)) & 0xFFFFFFFF)
     M = np.uint64(0xFFFFFFFF)
     for _ in range(10):
         p0 = np.uint64(0xD2511F53) * c0
@@ -224,6 +226,24 @@ def _resolve_init(env_params, B, A, O):
     raise ValueError(method)
 
 
+def noise_constants(init):
+    """(cholesky factor, multiplier, angle range) of the noisy agent reset, computed with the same
+    float32 torch ops as TriangleIntitializer.__init__ (utils.py:370-373: MultivariateNormal keeps
+    scale_tril = cholesky(diag(ags_std, ags_std)))."""
+    import torch
+    chol = torch.linalg.cholesky(torch.diag(torch.tensor([init['ags_std'], init['ags_std']])))
+    return float(chol[0, 0]), float(init['ags_dist']), float(np.float32(init['angle_range']))
+
+
+def agent_draws(seed, step_counter, env_id_offset, B, A):
+    """The addressed draws of the noisy agent reset: standard normals (B,A,2), uniforms (B,A)."""
+    normals = np.empty((B, A, 2), np.float32)
+    uniforms = np.empty((B, A), np.float32)
+    lib().mo_agent_draws(ctypes.c_uint64(seed), ctypes.c_uint64(step_counter), ctypes.c_uint64(env_id_offset),
+                         ctypes.c_int64(B), ctypes.c_int(A), _p(normals), _p(uniforms))
+    return normals, uniforms
+
+
 class OracleEnv:
     """C-oracle environment with the reference's Env surface (numpy tensors)."""
 
@@ -237,8 +257,15 @@ class OracleEnv:
         self.mode, ts, to, tt = _resolve_init(env_params, B, A, O)
         self.tmpl_states, self.tmpl_obstacles, self.tmpl_target = ts, to, tt
         self.counter = 0
+        init = env_params['init']
+        self.noisy = bool(init.get('noisy_ags')) and self.mode == 'shared'
+        self.noise = noise_constants(init) if self.noisy else (0.0, 0.0, 0.0)
         if self.mode == 'shared':
             self.states = np.broadcast_to(ts, (B, A, 5)).copy()
+            if self.noisy:
+                rs = self._reset_spec(0)
+                lib().mo_noisy_agents(ctypes.byref(rs), ctypes.c_uint64(0), ctypes.c_int64(B), ctypes.c_int(A),
+                                      _p(self.states))
             self.obstacles = philox_obstacles(self.p, self.seed, 0, self.env_id_offset)
             self.target = np.broadcast_to(tt, (B, 2)).copy()
         else:
@@ -262,9 +289,7 @@ class OracleEnv:
     def observations(self):
         return _obs_fields(self.observations_fused(), self.A, self.O)
 
-    def step_fused(self, actions, want_pre=False):
-        actions = np.ascontiguousarray(actions, np.float32).reshape(self.B, self.A, 2)
-        self.counter += 1
+    def _reset_spec(self, counter):
         rs = MoReset()
         rs.tmpl_states = _p(self.tmpl_states).value
         rs.tmpl_obstacles = _p(self.tmpl_obstacles).value if self.tmpl_obstacles is not None else None
@@ -273,8 +298,16 @@ class OracleEnv:
         rs.states_env_stride = self.A * 5 if per_env else 0
         rs.obstacles_env_stride = self.O * 2 if per_env else 0
         rs.target_env_stride = 2 if per_env else 0
-        rs.alias_first_step = 1 if self._alias else 0
-        rs.seed, rs.step_counter, rs.env_id_offset = self.seed, self.counter, self.env_id_offset
+        rs.alias_first_step = 1 if getattr(self, '_alias', False) else 0
+        rs.seed, rs.step_counter, rs.env_id_offset = self.seed, counter, self.env_id_offset
+        rs.noisy = 1 if self.noisy else 0
+        rs.noise_chol, rs.noise_mult, rs.angle_range = self.noise
+        return rs
+
+    def step_fused(self, actions, want_pre=False):
+        actions = np.ascontiguousarray(actions, np.float32).reshape(self.B, self.A, 2)
+        self.counter += 1
+        rs = self._reset_spec(self.counter)
         obs = np.empty((self.B, self.A, self.S), np.float32)
         pre = np.empty_like(obs) if want_pre else None
         rew = np.empty(self.B, np.float32)

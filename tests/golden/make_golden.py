@@ -258,6 +258,55 @@ def models_case(name):
     save(name, dict(torch=torch.__version__), arrays)
 
 
+class NoisyAgentsInjector:
+    """The REAL TriangleIntitializer with noisy_ags = True (utils.py:25,381-388) fed addressed draws:
+    its `pos_noise.sample()` gets the Philox/Box-Muller normals through torch.distributions' own
+    `_standard_normal` hook and its `torch.rand(B, 3)` the Philox uniforms, so everything it
+    computes from them -- scale_tril @ eps, ags_dist * ., angle_range * (u - 0.5), the vmapped
+    rotation, the cat -- is the reference's own code.  Obstacles: the addressed draw as elsewhere."""
+
+    def __init__(self, ref_init, params, seed):
+        self.ref, self.seed, self.counter = ref_init, int(seed), 0
+        self.p = orc.make_params(params)
+        assert ref_init.noisy_ags == 1
+
+    def __call__(self):
+        import torch.distributions.multivariate_normal as mvn
+        B = self.ref.num_parallel
+        normals, uniforms = orc.agent_draws(self.seed, self.counter, 0, B, 3)
+        saved = (mvn._standard_normal, torch.rand)
+        mvn._standard_normal = lambda shape, dtype, device: torch.from_numpy(normals).reshape(tuple(shape)).clone()
+        torch.rand = lambda *a, **k: torch.from_numpy(uniforms).clone()
+        try:
+            states = self.ref._sample_agents()
+        finally:
+            mvn._standard_normal, torch.rand = saved
+        obst = orc.philox_obstacles(self.p, self.seed, self.counter, 0)
+        self.counter += 1
+        return states, torch.from_numpy(obst), self.ref.target
+
+
+def noisy_case(name, B, steps, seed, act_seed, patched):
+    """SURVEY 8(f)-4's last piece: the triangle initialiser with its Gaussian position noise and
+    heading rotation switched on (`noisy_ags`, hard-coded False at utils.py:25), free-running."""
+    acts = actions_for(B, 3, steps, act_seed)
+    ctx = refload.oracle_trig() if patched else torch.no_grad()
+    with ctx:
+        args = refload.reference_args(num_parallel=B, num_agents=3, num_obstacles=3, episode_len=60)
+        params = copy.deepcopy(utils_mod.set_params(args)['env'])
+        params['init']['noisy_ags'] = True
+        env = env_mod.Env(params)
+        inj = NoisyAgentsInjector(env._init_sampler, params, seed)
+        env._init_sampler = inj
+        env.states, env.obstacles, env.target = inj()
+        init = dict(init_states=env.states.numpy().copy(), init_obstacles=env.obstacles.numpy().copy(),
+                    init_obs=fused(env.observations()))
+        arr = run_trace(env, acts, record_pre=not patched)
+    arr.update(init)
+    arr['actions'] = np.stack([a.numpy() for a in acts])
+    save(name, dict(B=B, A=3, O=3, steps=steps, seed=seed, act_seed=act_seed, angle=0.2, episode_len=60, noisy=1), arr)
+
+
 def quirk_case(name):
     """delayed target termination, collision+target,
     truncation -- 4 hand-placed envs, stock reference, constant action [0, -10]."""
@@ -289,6 +338,9 @@ if __name__ == '__main__':
             snm1_case('stock_rc_snm1', 0, patched=False)
         if 'models' in only:
             models_case('ref_models')
+        if 'noisy' in only:
+            noisy_case('patched_noisy_3x3', 24, 200, seed=11, act_seed=77, patched=True)
+            noisy_case('stock_noisy_3x3', 24, 80, seed=11, act_seed=77, patched=False)
         sys.exit(0)
     random_case('patched_tri_3x3', 48, 3, 3, 260, seed=7, act_seed=1234, patched=True)
     random_case('patched_tri_3x3_wide', 16, 3, 3, 60, seed=8, act_seed=99, patched=True, angle=4.0)
@@ -308,3 +360,5 @@ if __name__ == '__main__':
     snm1_case('patched_rc_snm1', 0, patched=True)
     snm1_case('stock_rc_snm1', 0, patched=False)
     models_case('ref_models')
+    noisy_case('patched_noisy_3x3', 24, 200, seed=11, act_seed=77, patched=True)
+    noisy_case('stock_noisy_3x3', 24, 80, seed=11, act_seed=77, patched=False)

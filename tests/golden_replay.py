@@ -27,6 +27,8 @@ def params_for(meta, make_default, make_template, **over):
     else:
         p = make_default(B, A, O, sampling_style="policy")
     p["episode_len"] = int(meta.get("episode_len", 200))
+    if int(meta.get("noisy", 0)):
+        p["init"]["noisy_ags"] = True            # utils.py:25 switched on
     p.update(over)
     return p
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.marlnav_abi_version() == 3
+    assert lib.marlnav_abi_version() == 4
     assert lib.marlnav_obs_size(3, 3) == 12 and lib.marlnav_obs_size(8, 16) == 48
     assert lib.marlnav_obs_size(1, 3) == 0 and lib.marlnav_obs_size(3, 0) == 0
     assert lib.marlnav_obs_size(27, 3) == 0
@@ -29,12 +29,43 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from marlnav_b200 import _lib
-    assert ctypes.sizeof(_lib.EnvParams) == 4 * 4 + 27 * 4
-    assert ctypes.sizeof(_lib.ResetSpec) == 3 * 8 + 3 * 8 + 8 + 3 * 8 + 8
-    assert ctypes.sizeof(_lib.IoTransform) == 4 * 8
+    assert ctypes.sizeof(_lib.EnvParams) == 4 + 4 * 4 + 27 * 4
+    assert ctypes.sizeof(_lib.ResetSpec) == 8 + 3 * 8 + 3 * 8 + 4 + 3 * 4 + 3 * 8 + 8
+    assert ctypes.sizeof(_lib.IoTransform) == 8 + 4 * 8
+    assert ctypes.sizeof(_lib.ActorSpec) == 8 + 6 * 8 + 2 * 4 + 2 * 8 + 8 + 8
     from oracle import oracle as orc
-    assert ctypes.sizeof(orc.MoParams) == ctypes.sizeof(_lib.EnvParams)
-    assert [f[0] for f in orc.MoParams._fields_] == [f[0] for f in _lib.EnvParams._fields_]
+    assert ctypes.sizeof(orc.MoParams) + 4 == ctypes.sizeof(_lib.EnvParams)
+    assert [f[0] for f in orc.MoParams._fields_] == [f[0] for f in _lib.EnvParams._fields_][1:]
+    # the library reports the sizes of ITS build: a binding compares them with its own layouts
+    lib = _lib.load()
+    for cls, fn in ((_lib.EnvParams, lib.marlnav_sizeof_env_params), (_lib.ResetSpec, lib.marlnav_sizeof_reset_spec),
+                    (_lib.IoTransform, lib.marlnav_sizeof_io_transform), (_lib.ActorSpec, lib.marlnav_sizeof_actor_spec)):
+        assert fn() == ctypes.sizeof(cls) == cls().struct_size
+
+
+def test_short_or_stale_structs_are_rejected():
+    """ABI 4: every struct carries its size; a binding built against an older layout (e.g. the
+    ABI-2 reset spec without step_counter_dev) gets MARLNAV_ERR_BAD_ARG, not an out-of-bounds read."""
+    from marlnav_b200 import _lib
+    lib = _lib.load()
+    p = _lib.EnvParams(); p.num_envs, p.num_agents, p.num_obstacles = 64, 3, 3
+    rs = _lib.ResetSpec(); rs.alias_first_step = 1
+    rs.struct_size -= 8                                   # a struct that stops before step_counter_dev
+    dummy = ctypes.c_void_p(16)
+    rc = lib.marlnav_step_f32(ctypes.byref(p), ctypes.byref(rs), *([dummy] * 11), None, None)
+    assert rc == -1 and b"marlnav_reset_spec.struct_size" in lib.marlnav_last_error()
+    rs = _lib.ResetSpec(); rs.alias_first_step = 1
+    p.struct_size = 0
+    rc = lib.marlnav_step_f32(ctypes.byref(p), ctypes.byref(rs), *([dummy] * 11), None, None)
+    assert rc == -1 and b"marlnav_env_params.struct_size" in lib.marlnav_last_error()
+    p = _lib.EnvParams(); p.num_envs, p.num_agents, p.num_obstacles = 64, 3, 3
+    io = _lib.IoTransform(); io.struct_size = 32
+    rc = lib.marlnav_step_f32(ctypes.byref(p), ctypes.byref(rs), *([dummy] * 11), ctypes.byref(io), None)
+    assert rc == -1 and b"marlnav_io_transform.struct_size" in lib.marlnav_last_error()
+    rs.flags = _lib.RESET_NOISY_AGENTS; rs.alias_first_step = 0; rs.tmpl_states = 16; rs.tmpl_target = 16
+    rs.states_env_stride = 15
+    rc = lib.marlnav_step_f32(ctypes.byref(p), ctypes.byref(rs), *([dummy] * 11), None, None)
+    assert rc == -1 and b"NOISY" in lib.marlnav_last_error()
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -58,7 +89,6 @@ def test_fused_actor_step_argument_errors_and_small_batch_geometry():
     laid out thread-per-agent (8 envs per one-warp CTA), a large one thread-per-env (32)."""
     from marlnav_b200 import _lib
     lib = _lib.load()
-    assert ctypes.sizeof(_lib.ActorSpec) == 6 * 8 + 2 * 4 + 2 * 8 + 8
     p = _lib.EnvParams(); p.num_envs, p.num_agents, p.num_obstacles = 64, 3, 3
     rs = _lib.ResetSpec(); rs.alias_first_step = 1
     rc = lib.marlnav_act_step_f32(ctypes.byref(p), ctypes.byref(rs), *([None] * 16))

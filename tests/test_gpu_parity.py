@@ -205,3 +205,108 @@ def test_host_stepper_matches_device_step(oracle):
         assert torch.equal(term.cpu(), hs.terminated_host.bool())
         assert torch.equal(trunc.cpu(), hs.truncated_host.bool())
     assert torch.equal(e1.states, e2.states)
+
+
+# ----------------------------------------------------------------------------- round 2 additions
+
+@pytest.mark.parametrize("make", ["tri_small", "tri_large", "ring_8x16", "ring_4x2"])
+def test_noisy_agents_free_running(oracle, make):
+    """noisy_ags = True (utils.py:25,381-388): Gaussian position noise + heading
+    rotation on every (re-)initialised agent, in all three step kernels and the init kernel --
+    thread-per-agent team of 3 (small batch), thread-per-env (large batch), (8,16) team, generic."""
+    import marlnav_b200 as mb
+    if make == "tri_small":
+        p = mb.default_env_params(777, 3, 3, sampling_style='policy', episode_len=40)
+    elif make == "tri_large":
+        p = mb.default_env_params(20000, 3, 3, sampling_style='policy', episode_len=40)
+    elif make == "ring_8x16":
+        p = mb.template_env_params(301, 8, 16, episode_len=40)
+    else:
+        p = mb.template_env_params(200, 4, 2, episode_len=40)
+    p['init']['noisy_ags'] = True
+    ndone = _run_free(p, oracle, steps=100, check_every=1 if make != "tri_large" else 7)
+    assert ndone > p['num_parallel']                # every env was re-initialised at least once
+
+
+def test_sharded_equals_single_8_shards_and_noisy(oracle):
+    """BASELINE configs[3]'s split: eight slices with env_id_offset reproduce one full-size Env
+    bit for bit -- also with the noisy agent reset, whose draws are addressed by global env id."""
+    import marlnav_b200 as mb
+    full = mb.default_env_params(1000, 3, 3, sampling_style='policy', episode_len=50)
+    full['init']['noisy_ags'] = True
+    e_full = _mk(full, 5)
+    shards = [_mk(mb.shard_env_params(full, r, 8), 5) for r in range(8)]
+    bounds = [mb.shard_bounds(1000, r, 8) for r in range(8)]
+    assert torch.equal(e_full.states, torch.cat([s.states for s in shards]))
+    pool = action_pool(1000, 3)
+    for t in range(120):
+        act = pool[t % len(pool)].cuda()
+        o, r, te, tr = e_full.step_fused(act)
+        parts = [s.step_fused(act[lo:lo + n].contiguous()) for s, (lo, n) in zip(shards, bounds)]
+        for k, full_t in enumerate((o, r, te, tr)):
+            assert torch.equal(full_t, torch.cat([p[k] for p in parts])), (t, k)
+    assert torch.equal(e_full.states, torch.cat([s.states for s in shards]))
+    assert torch.equal(sum(s.episode_stats for s in shards), e_full.episode_stats)
+    assert int(e_full.episode_stats.sum()) > 1000
+
+
+@pytest.mark.parametrize("A,O,B", [(3, 3, 4096), (3, 3, 100000), (8, 16, 1024), (4, 2, 512)])
+def test_misaligned_base_pointers(oracle, A, O, B):
+    """Tensors whose base pointers are only 4-byte aligned (vec_ok == 0): the kernels must take their
+    plain-load staging paths instead of TMA bulk copies / float4 accesses, with the same results."""
+    import marlnav_b200 as mb
+    p = mb.default_env_params(B, A, O, sampling_style='policy') if A == 3 else mb.template_env_params(B, A, O)
+    env = _mk(p, 7)
+    oe = oracle.OracleEnv(cpu_params(p), seed=7)
+
+    def shifted(t):          # same values, storage offset by one float
+        flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)[1:]
+        flat.copy_(t.reshape(-1))
+        return flat.view(t.shape)
+    env.states, env.obstacles, env.target = shifted(env.states), shifted(env.obstacles), shifted(env.target)
+    assert env.states.data_ptr() % 16 == 4 and env.states.is_contiguous()
+    S = env.obs_size
+    obs = torch.empty(B * A * S + 1, device='cuda')[1:].view(B, A, S)
+    rew = torch.empty(B, device='cuda')
+    term = torch.empty(B, dtype=torch.uint8, device='cuda'); trunc = torch.empty_like(term)
+    pool = action_pool(B, A)
+    for t in range(40):
+        act = torch.empty(B * A * 2 + 1, device='cuda')[1:].view(B, A, 2)
+        act.copy_(pool[t % len(pool)])
+        env.step_fused(act, out=(obs, rew, term, trunc))
+        o_obs, o_rew, o_term, o_trunc = oe.step_fused(pool[t % len(pool)].numpy())
+        if t % 5 == 0 or t == 39:
+            assert_bits_equal(f"step {t} obs", obs.cpu().numpy(), o_obs)
+            assert_bits_equal(f"step {t} rewards", rew.cpu().numpy(), o_rew)
+            assert_bits_equal(f"step {t} term", term.cpu().numpy().astype(bool), o_term)
+    _compare_state(env, oe, "final")
+    assert_bits_equal("observe", env.observations_fused().cpu().numpy(), oe.observations_fused())
+
+
+def test_step_outputs_are_fresh_until_released(oracle):
+    """Env.step hands out tensors from reusable output slots: a slot is only recycled when the caller
+    holds none of its tensors (models.py:121 keeps every step's rewards by reference)."""
+    import marlnav_b200 as mb
+    p = mb.default_env_params(64, 3, 3, sampling_style='policy')
+    env = _mk(p, 3)
+    oe = oracle.OracleEnv(cpu_params(p), seed=3)
+    pool = action_pool(64, 3)
+    kept, want = [], []
+    for t in range(30):                                  # MAPPO.get_data: keeps rewards, done; drops obs
+        obs, rew, term, trunc = env.step(pool[t % 8].cuda())
+        o_obs, o_rew, o_term, o_trunc = oe.step_fused(pool[t % 8].numpy())
+        kept.append((rew, obs.others_distances[:, 0]))   # a tensor, and a view of a view
+        want.append((o_rew, o_obs[:, 0, 10:12]))
+    torch.cuda.synchronize()
+    for (rew, od), (o_rew, o_od) in zip(kept, want):
+        assert_bits_equal("kept rewards", rew.cpu().numpy(), o_rew)
+        assert_bits_equal("kept view", od.cpu().numpy(), o_od)
+    assert len({r.data_ptr() for r, _ in kept}) == 30   # thirty different buffers
+    n_slots = len(env._ring)
+    del kept, rew, obs, term, trunc, od
+    ptrs = set()
+    for t in range(200):                                 # nothing kept: the ring stops growing
+        obs, rew, term, trunc = env.step(pool[t % 8].cuda())
+        ptrs.add(rew.data_ptr())
+        del obs, rew, term, trunc
+    assert len(env._ring) <= n_slots + 1 and len(ptrs) <= n_slots + 1

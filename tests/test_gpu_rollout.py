@@ -258,3 +258,58 @@ def test_step_graph_replays_continue_the_eager_loop(B, keep):
     assert torch.equal(env.states, eager.states) and torch.equal(env.obstacles, eager.obstacles)
     env.use_device_counter(False)
     assert env._reset_counter == eager._reset_counter
+
+
+def test_sharded_rollout_equals_single_process():
+    """The actor's sampling noise is addressed by GLOBAL (env, agent) row (marlnav_actor_spec.row_offset,
+    ABI 4): two ranks' rollouts of two half batches are the single-process rollout, bit for bit --
+    with the fused {actor -> step} launch and with the two-launch route."""
+    import marlnav_b200 as mb
+    B, A, O, T = 600, 3, 3, 60
+    S = 2 + 2 * O + 2 * (A - 1)
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm, scal = dict(min_obs=lo, max_obs=hi), dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    w = _actor_weights(S, 50)
+    full = mb.default_env_params(B, A, O, sampling_style='policy', episode_len=25); full['seed'] = 8
+    for fuse in (True, False):
+        env = mb.Env(dict(full)); env.fuse_io(norm, scal)
+        whole = mb.collect_rollout(env, mb.FusedActor(w, seed=13), T, fuse_actor=fuse)
+        parts = []
+        for r in range(2):
+            e = mb.Env(mb.shard_env_params(full, r, 2)); e.fuse_io(norm, scal)
+            parts.append(mb.collect_rollout(e, mb.FusedActor(w, seed=13), T, fuse_actor=fuse))
+        for key, dim in (('obs', 1), ('actions', 1), ('log_probs', 1), ('rewards', 1), ('done', 1)):
+            assert torch.equal(whole[key], torch.cat([p[key] for p in parts], dim=dim)), (fuse, key)
+        assert bool(whole['done'].any())
+
+
+@pytest.mark.parametrize("B", [1, 5, 33, 1000, 16385, 20001])
+def test_fused_actor_step_ragged_batches(B):
+    """Batches that are not a multiple of the tile (8 envs per warp thread-per-agent, 32 thread-per-env)
+    through the fused {actor -> step} launch == the two-launch route."""
+    import marlnav_b200 as mb
+    A, O, T = 3, 3, 24
+    S = 12
+    max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
+    lo = [-math.pi, 0.] + O * [-math.pi] + O * [0.] + (A - 1) * [-math.pi] + (A - 1) * [0.]
+    hi = [math.pi, max_d] + O * [math.pi] + O * [max_d] + (A - 1) * [math.pi] + (A - 1) * [max_d]
+    norm, scal = dict(min_obs=lo, max_obs=hi), dict(min_action=[-math.pi, -0.5], max_action=[math.pi, 0.5])
+    w = _actor_weights(S, 50)
+    bufs = []
+    for fuse in (True, False):
+        p = mb.default_env_params(B, A, O, sampling_style='policy', episode_len=10); p['seed'] = 2
+        env = mb.Env(p); env.fuse_io(norm, scal)
+        bufs.append(mb.collect_rollout(env, mb.FusedActor(w, seed=4), T, fuse_actor=fuse))
+    for key in ('obs', 'last_obs', 'actions', 'log_probs', 'rewards', 'done'):
+        assert torch.equal(bufs[0][key], bufs[1][key]), key
+
+
+def test_actor_accepts_its_largest_advertised_shape():
+    """S = 48 (the (8,16) team) with H = 256 needs 54 KiB of dynamic shared memory (> the 48 KiB default)."""
+    import marlnav_b200 as mb
+    w = _actor_weights(48, 256)
+    obs = torch.rand(100, 48) * 2 - 1
+    act, lp = mb.FusedActor(w, seed=1).act(obs.cuda())
+    assert bool(torch.isfinite(act).all()) and bool(torch.isfinite(lp).all())
