@@ -41,6 +41,8 @@ from .params import GEOMETRY
 from .samplers import action_sampler
 
 _storage_use_count = getattr(torch._C, '_storage_Use_Count', None)     # tensors sharing a storage
+if not getattr(sys, '_is_gil_enabled', lambda: True)():                 # (reference counts are exact only with the GIL)
+    _storage_use_count = None
 
 
 
@@ -443,25 +445,29 @@ class Env(object):
         objs = (obs, rew, tb, cb, fields) + tuple(fields)
         slot = dict(obs=obs, rew=rew, term=tb, trunc=cb, fields=fields, storage=storage, objs=objs,
                     ptrs=(obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr()),
-                    nbytes=storage.nbytes(), u8=(term, trunc), call=_lib.StepCall(), epoch=0)
+                    nbytes=storage.nbytes(), u8=(term, trunc), call=_lib.StepCall(), epoch=0, stream=None)
         del obs, rew, term, trunc, fields, tb, cb
         slot['rest'] = _refcounts(objs)
         slot['shared'] = _storage_use_count(storage._cdata) if _storage_use_count else -1
         return slot
 
-    def _slot_free(self, slot):
-        if not _storage_use_count or _storage_use_count(slot['storage']._cdata) != slot['shared']:
+    def _slot_free(self, slot, stream):
+        # (like torch's caching allocator, a buffer is only recycled on the stream it was used on)
+        if slot['stream'] != stream or not _storage_use_count or \
+                _storage_use_count(slot['storage']._cdata) != slot['shared']:
             return False
         return _refcounts(slot['objs']) == slot['rest']
 
     def _take_slot(self):
         ring = self._ring
+        stream = self._raw_stream() if torch.cuda.current_device() == self.device.index else -1
         for _ in range(min(len(ring), 3)):        # (a few tries: a caller may be holding some slots for long)
             slot = ring[0]
             ring.rotate(-1)
-            if self._slot_free(slot):
+            if self._slot_free(slot, stream):
                 return slot
         slot = self._new_slot()
+        slot['stream'] = stream
         if len(ring) < self._RING_MAX_SLOTS and self._ring_bytes + slot['nbytes'] <= self._RING_MAX_BYTES:
             ring.append(slot)
             self._ring_bytes += slot['nbytes']

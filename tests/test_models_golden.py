@@ -64,10 +64,10 @@ def test_fused_actor_matches_reference_models(tag):
     t, actor, _ = _case(z, tag)
     obs = t("obs")
     act, lp, mu, var = mb.FusedActor(actor, seed=1).act(obs.cuda(), eps=t("eps"), want_moments=True)
-    np.testing.assert_allclose(mu.cpu().numpy(), z[f"{tag}_mu"], rtol=2e-5, atol=5e-6)
-    np.testing.assert_allclose(var.cpu().numpy(), z[f"{tag}_var"], rtol=2e-5, atol=5e-6)
-    np.testing.assert_allclose(act.cpu().numpy(), z[f"{tag}_actions"], rtol=2e-5, atol=1e-5)
-    np.testing.assert_allclose(lp.cpu().numpy(), z[f"{tag}_log_probs"], rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(mu.cpu().numpy(), z[f"{tag}_mu"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(var.cpu().numpy(), z[f"{tag}_var"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(act.cpu().numpy(), z[f"{tag}_actions"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(lp.cpu().numpy(), z[f"{tag}_log_probs"], rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.gpu
