@@ -310,3 +310,14 @@ def test_step_outputs_are_fresh_until_released(oracle):
         ptrs.add(rew.data_ptr())
         del obs, rew, term, trunc
     assert len(env._ring) <= n_slots + 1 and len(ptrs) <= n_slots + 1
+
+
+@pytest.mark.parametrize("A,O,B", [(3, 3, 3000), (3, 3, 20000), (8, 16, 300)])
+def test_zero_clamp_bounds(oracle, A, O, B):
+    """min_accel = 0 / min_speed = 0: torch.clamp's `(a < b) ? b : a` keeps a -0 against a +0 bound (a
+    two-FMNMX clamp would not; measured no faster and not used)."""
+    import marlnav_b200 as mb
+    p = mb.default_env_params(B, A, O, sampling_style='policy') if A == 3 else mb.template_env_params(B, A, O)
+    p.update(min_accel=0.0, min_speed=0.0)
+    ndone = _run_free(p, oracle, steps=80, check_every=4)
+    assert ndone > 0
