@@ -31,26 +31,14 @@ Differences from the reference, all documented in DESIGN.md:
 """
 import ctypes
 import math
-import sys
-from collections import deque, namedtuple
+from collections import namedtuple
 
 import torch
 
 from . import _lib
 from .params import GEOMETRY
 from .samplers import action_sampler
-
-_storage_use_count = getattr(torch._C, '_storage_Use_Count', None)     # tensors sharing a storage
-if not getattr(sys, '_is_gil_enabled', lambda: True)():                 # (reference counts are exact only with the GIL)
-    _storage_use_count = None
-
-
-
-def _refcounts(objs, _getref=sys.getrefcount):
-    """Reference counts of a slot's tensors; baseline and check go through this one function so
-    that the temporaries of the counting itself cancel."""
-    return [_getref(o) for o in objs]
-
+from .slots import OutputSlots
 
 # Same type the reference returns (utils.py:13-15).
 Observations = namedtuple('Observations', ['target_angle', 'target_distance',
@@ -139,8 +127,7 @@ class Env(object):
         self._setup_reset_source(params['init'])
 
         B, A, O = self.num_parallel, self.num_agents, self.num_obstacles
-        self._ring = deque()              # reusable output slots of step() (see _take_slot)
-        self._ring_bytes = 0
+        self._ring = OutputSlots(self._new_slot)      # reusable output slots of step()
         with torch.cuda.device(dev):
             self._states = torch.empty(B, A, 5, device=dev)
             self._obstacles = torch.empty(B, O, 2, device=dev)
@@ -425,53 +412,21 @@ class Env(object):
         trunc = buf[n_obs + n_rew + n_flag:n_obs + n_rew + n_flag + B]
         return obs, rew, term, trunc
 
-    # ---- output slots.  step() must hand out FRESH tensors (the reference's rollout buffer keeps a
-    # reference to every step's rewards, models.py:121), but allocating them and cutting the six
-    # Observations views costs more host time than the launch at small batches.  A slot = one
-    # buffer with all its views prebuilt; a slot is handed out again only when nobody outside holds
-    # any of its tensors: every Python object of the slot is back at its resting reference count
-    # AND the buffer's storage is shared by no tensor beyond the slot's own (a caller's slice of a
-    # slice is a new tensor on the same storage).  Busy slots are skipped and a new one is made, so
-    # a caller that keeps T steps simply grows the ring to T slots (capped; past the cap, or on a
-    # torch without the storage use-count hook, plain allocation every step).
-    _RING_MAX_SLOTS = 4096
-    _RING_MAX_BYTES = 2 << 30
+    # ---- output slots (marlnav_b200/slots.py): buffers with prebuilt views and launch arguments,
+    # recycled only when the caller holds none of their tensors
 
     def _new_slot(self):
         obs, rew, term, trunc = self._alloc_outputs()
         fields = split_observations(obs, self.num_agents, self.num_obstacles)
         tb, cb = term.view(torch.bool), trunc.view(torch.bool)
-        storage = obs.untyped_storage()
-        objs = (obs, rew, tb, cb, fields) + tuple(fields)
-        slot = dict(obs=obs, rew=rew, term=tb, trunc=cb, fields=fields, storage=storage, objs=objs,
+        return dict(obs=obs, rew=rew, term=tb, trunc=cb, fields=fields, storage=obs.untyped_storage(),
+                    objs=(obs, rew, tb, cb, fields) + tuple(fields),
                     ptrs=(obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr()),
-                    nbytes=storage.nbytes(), u8=(term, trunc), call=_lib.StepCall(), epoch=0, stream=None)
-        del obs, rew, term, trunc, fields, tb, cb
-        slot['rest'] = _refcounts(objs)
-        slot['shared'] = _storage_use_count(storage._cdata) if _storage_use_count else -1
-        return slot
-
-    def _slot_free(self, slot, stream):
-        # (like torch's caching allocator, a buffer is only recycled on the stream it was used on)
-        if slot['stream'] != stream or not _storage_use_count or \
-                _storage_use_count(slot['storage']._cdata) != slot['shared']:
-            return False
-        return _refcounts(slot['objs']) == slot['rest']
+                    u8=(term, trunc), call=_lib.StepCall(), epoch=0)
 
     def _take_slot(self):
-        ring = self._ring
         stream = self._raw_stream() if torch.cuda.current_device() == self.device.index else -1
-        for _ in range(min(len(ring), 3)):        # (a few tries: a caller may be holding some slots for long)
-            slot = ring[0]
-            ring.rotate(-1)
-            if self._slot_free(slot, stream):
-                return slot
-        slot = self._new_slot()
-        slot['stream'] = stream
-        if len(ring) < self._RING_MAX_SLOTS and self._ring_bytes + slot['nbytes'] <= self._RING_MAX_BYTES:
-            ring.append(slot)
-            self._ring_bytes += slot['nbytes']
-        return slot
+        return self._ring.take(stream)
 
     def _step_call_cache(self):
         """Launch arguments that do not change between steps (state tensors are updated in place;

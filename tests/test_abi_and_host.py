@@ -204,3 +204,41 @@ def test_reduce_is_noop_without_process_group():
     assert mb.reduce_episode_stats(s).tolist() == [1, 2, 3]
     with pytest.raises(ValueError):
         mb.reduce_episode_stats(torch.zeros(3))
+
+
+def test_output_slots_are_recycled_only_when_released():
+    """marlnav_b200/slots.py on CPU tensors: a slot comes back only when the caller holds neither one of
+    its tensors, nor the namedtuple, nor a view of a view, and only on the stream it was used on."""
+    from marlnav_b200.env import split_observations
+    from marlnav_b200.slots import OutputSlots, _storage_use_count
+    if _storage_use_count is None:
+        pytest.skip("this torch has no storage use-count hook: slots are never recycled")
+    B, A, O = 8, 3, 3
+    S = 2 + 2 * O + 2 * (A - 1)
+
+    def make():
+        buf = torch.empty(B * A * S * 4 + 64, dtype=torch.uint8)
+        obs = buf[:B * A * S * 4].view(torch.float32).view(B, A, S)
+        rew = buf[B * A * S * 4:B * A * S * 4 + 32].view(torch.float32)
+        fields = split_observations(obs, A, O)
+        return dict(obs=obs, rew=rew, fields=fields, storage=obs.untyped_storage(), objs=(obs, rew, fields) + tuple(fields))
+
+    pool = OutputSlots(make)
+    a = pool.take(stream=7)
+    ident = id(a)
+    del a
+    assert id(pool.take(7)) == ident and len(pool) == 1            # released -> the same slot again
+    held = [pool.take(7)['rew'] for _ in range(5)]                 # MAPPO.get_data keeps every step's rewards
+    assert len({r.data_ptr() for r in held}) == 5 and len(pool) == 5
+    view = held[0][1:2][0:1]                                       # a view of a view
+    field = pool.take(7)['fields'].others_distances                # one Observations field
+    del held
+    busy = sum(not pool.is_free(s, 7) for s in pool._ring)
+    assert busy == 2                                               # exactly the two slots still referenced
+    n = len(pool)
+    for _ in range(50):
+        s = pool.take(7); assert s['rew'].data_ptr() not in (view.data_ptr() - 4, ) ; del s
+    assert len(pool) <= n + 2                                      # busy slots are skipped, the ring stops growing
+    del view, field
+    assert all(pool.is_free(s, 7) for s in pool._ring)
+    assert not any(pool.is_free(s, 8) for s in pool._ring)         # another stream: never recycled there
