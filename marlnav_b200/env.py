@@ -81,8 +81,10 @@ class Env(object):
         if dev.index is None:
             dev = torch.device('cuda', torch.cuda.current_device())
         self.device = dev
+        self._dev_index = dev.index
         self.num_parallel = int(params['num_parallel'])
         self.num_agents = int(params['num_agents'])
+        self._n_action_floats = self.num_parallel * self.num_agents * 2
         self.num_obstacles = int(params['num_obstacles'])
         self.max_step = params['max_step']
         self.episode_len = int(params['episode_len'])
@@ -158,7 +160,7 @@ class Env(object):
     def _raw_stream(self):
         """cudaStream_t of torch's current stream on this device, as an int."""
         try:
-            return torch._C._cuda_getCurrentRawStream(self.device.index)
+            return torch._C._cuda_getCurrentRawStream(self._dev_index)
         except AttributeError:            # (private fast path; the public route costs ~1.5 us more)
             return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -425,8 +427,12 @@ class Env(object):
                     u8=(term, trunc), call=_lib.StepCall(), epoch=0)
 
     def _take_slot(self):
-        stream = self._raw_stream() if torch.cuda.current_device() == self.device.index else -1
-        return self._ring.take(stream)
+        """-> (slot, stream): the raw current stream when this env's device is current, else None
+        (the launch then switches devices itself and the slot is not shared with other streams)."""
+        if torch.cuda.current_device() == self._dev_index:
+            stream = self._raw_stream()
+            return self._ring.take(stream), stream
+        return self._ring.take(-1), None
 
     def _step_call_cache(self):
         """Launch arguments that do not change between steps (state tensors are updated in place;
@@ -452,15 +458,18 @@ class Env(object):
         call.io = ctypes.addressof(self._io) if self._io is not None else None
         return call
 
-    def _launch_step(self, actions, ptrs, slot=None):
-        """One fused step launch writing to the four output pointers `ptrs` (or to `slot`'s)."""
+    def _launch_step(self, actions, ptrs, slot=None, stream=None):
+        """One fused step launch writing to the four output pointers `ptrs` (or to `slot`'s), on
+        `stream` (raw handle of the current stream of this env's device; None = look it up)."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
-        if actions.numel() != self.num_parallel * self.num_agents * 2:
+        if actions.numel() != self._n_action_floats:
             raise _lib.MarlnavError(f"actions must be ({self.num_parallel},{self.num_agents},2), got {tuple(actions.shape)}")
-        if torch.cuda.current_device() != self.device.index:
-            with torch.cuda.device(self.device):
-                return self._launch_step(actions, ptrs, slot)
+        if stream is None:
+            if torch.cuda.current_device() != self._dev_index:
+                with torch.cuda.device(self.device):
+                    return self._launch_step(actions, ptrs, slot)
+            stream = self._raw_stream()
         c = self._step_call_cache()
         if slot is not None:
             call = slot['call']
@@ -478,7 +487,6 @@ class Env(object):
         rs = c['rs']
         # the counters move only once the launch has been accepted
         counter_dev, batch = self._counter_dev, self._counter_batch
-        stream = self._raw_stream()
         if counter_dev is None:
             rs.step_counter = self._reset_counter + 1
         elif batch:
@@ -510,14 +518,14 @@ class Env(object):
             obs, rew, term, trunc = out
             self._launch_step(actions, (obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr()))
             return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
-        slot = self._take_slot()
-        self._launch_step(actions, None, slot)
+        slot, stream = self._take_slot()
+        self._launch_step(actions, None, slot, stream)
         return slot['obs'], slot['rew'], slot['term'], slot['trunc']
 
     def step(self, actions):
         """environment.py:92-107"""
-        slot = self._take_slot()
-        self._launch_step(actions, None, slot)
+        slot, stream = self._take_slot()
+        self._launch_step(actions, None, slot, stream)
         return slot['fields'], slot['rew'], slot['term'], slot['trunc']
 
     def launch_info(self):
