@@ -308,15 +308,15 @@ class Env(object):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             sp = actor.spec(actor._advance_counter(stream))
             sp.row_offset = self._env_id_offset * self.num_agents if actor.row_offset is None else actor.row_offset
-            self._reset_counter += 1
             rs = self._reset_spec(alias=self._alias_pending)
-            rs.step_counter = self._advance_device_counter()
+            rs.step_counter = self._next_step_counter(stream)
             _lib.check(self._lib.marlnav_act_step_f32(
                 ctypes.byref(self._c_params), ctypes.byref(rs), self._ptr(self.states), self._ptr(self.obstacles),
                 self._ptr(self.target), self._ptr(self._step_num), self._ptr(self._terminates_u8),
                 ctypes.byref(sp), obs_in.data_ptr(), actions.data_ptr(), log_probs.data_ptr(),
                 obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), self._ptr(self._stats),
                 ctypes.byref(self._io), stream), "marlnav_act_step_f32")
+            self._commit_step_counter()
             if self._alias_pending:
                 # the reference's template froze at "state after the first move" (B-6)
                 self._tmpl_states = self.states.clone()
@@ -324,18 +324,22 @@ class Env(object):
                 self.__dict__.pop('_call_cache', None)      # template pointer changed
         return actions, log_probs, obs, rew, term, trunc
 
-    def _advance_device_counter(self):
-        """The ``step_counter`` to pass for the step being launched (``_reset_counter`` was already
-        incremented).  Host counter: its value.  Device counter: 0 after bumping the device word, or,
-        in batch mode, the step's offset inside the batch (``flush_device_counter`` adds the total)."""
+    def _next_step_counter(self, stream):
+        """``step_counter`` argument of the step about to be launched; nothing on the host moves until
+        ``_commit_step_counter`` is called after the launch was accepted.  Host counter: its next value.
+        Device counter: 0 after bumping the device word on ``stream``, or, in batch mode, the step's
+        offset inside the batch (``flush_device_counter`` adds the total)."""
         if self._counter_dev is None:
-            return self._reset_counter
+            return self._reset_counter + 1
         if self._counter_batch:
-            self._counter_pending += 1
-            return self._counter_pending
-        self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1,
-                                      torch.cuda.current_stream(self.device).cuda_stream)
+            return self._counter_pending + 1
+        self._lib.marlnav_counter_add(self._counter_dev.data_ptr(), 1, stream)
         return 0
+
+    def _commit_step_counter(self):
+        self._reset_counter += 1
+        if self._counter_dev is not None and self._counter_batch:
+            self._counter_pending += 1
 
     def batch_device_counter(self, enable=True):
         """Batch mode of the device-resident counter: steps address their Philox draws as
@@ -485,15 +489,7 @@ class Env(object):
                     calls.clear()
                 call = calls[ptrs] = self._fill_call(_lib.StepCall(), c, ptrs)
         rs = c['rs']
-        # the counters move only once the launch has been accepted
-        counter_dev, batch = self._counter_dev, self._counter_batch
-        if counter_dev is None:
-            rs.step_counter = self._reset_counter + 1
-        elif batch:
-            rs.step_counter = self._counter_pending + 1
-        else:
-            self._lib.marlnav_counter_add(counter_dev.data_ptr(), 1, stream)
-            rs.step_counter = 0
+        rs.step_counter = self._next_step_counter(stream)      # the host counters move after the launch
         if self._alias_pending:
             rs.alias_first_step = 1
         call.actions = actions.data_ptr()
@@ -501,9 +497,7 @@ class Env(object):
         rc = c['fn'](ctypes.addressof(call))
         if rc:
             _lib.check(rc, "marlnav_step_call_f32")
-        self._reset_counter += 1
-        if batch and counter_dev is not None:
-            self._counter_pending += 1
+        self._commit_step_counter()
         if self._alias_pending:
             # the reference's template froze at "state after the first move" (B-6)
             self._tmpl_states = self._states.clone()
@@ -585,10 +579,9 @@ class HostStepper:
                 or src.numel() != self.actions_host.numel():
             raise _lib.MarlnavError("HostStepper.step needs a contiguous float32 CPU tensor of shape (B,A,2)")
         with torch.cuda.device(env.device):
-            env._reset_counter += 1
-            step_counter = env._advance_device_counter()
+            stream = torch.cuda.current_stream(env.device).cuda_stream
             rs = env._reset_spec(alias=env._alias_pending)
-            rs.step_counter = step_counter
+            rs.step_counter = env._next_step_counter(stream)
             _lib.check(env._lib.marlnav_step_host_f32(
                 self._pipe, ctypes.byref(env._c_params), ctypes.byref(rs),
                 p(env.states), p(env.obstacles), p(env.target), p(env._step_num), p(env._terminates_u8),
@@ -596,7 +589,8 @@ class HostStepper:
                 p(self.terminated_dev), p(self.truncated_dev),
                 p(self.obs_host), p(self.rewards_host), p(self.terminated_host), p(self.truncated_host),
                 p(env._stats), ctypes.byref(env._io) if env._io is not None else None,
-                env._stream()), "marlnav_step_host_f32")
+                ctypes.c_void_p(stream)), "marlnav_step_host_f32")
+            env._commit_step_counter()
             if env._alias_pending:
                 env._tmpl_states = env.states.clone()
                 env._alias_pending = False
