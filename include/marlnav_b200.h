@@ -85,7 +85,11 @@ typedef struct marlnav_env_params {
  *   alias_first_step != 0 -> reproduce MockInitializer's aliasing on the first
  *                    step: the template IS the current state. */
 /* flags: no element of a SHARED tmpl_states (states_env_stride == 0) has its sign bit set,
- * so 0*template == +0 and the blend of a not-reset env reduces to old + 0 (no template reads) */
+ * so 0*template == +0 and the blend of a not-reset env reduces to old + 0 (no template reads).
+ * A binding should set it whenever it holds (marlnav_b200.Env checks the template): together with
+ * states_env_stride == 0, alias_first_step == 0, no MARLNAV_RESET_NOISY_AGENTS and the reference's
+ * geometry constants it selects the step kernels specialised for the default reset source (1-2 %
+ * faster); every other combination runs the general kernels, with identical results. */
 #define MARLNAV_RESET_TMPL_NONNEG 1
 /* TriangleIntitializer with noisy_ags = True (utils.py:25, 381-388; shared template only): every
  * (re-)initialised agent gets Gaussian position noise  pos += noise_mult * (noise_chol * z)  with
