@@ -242,3 +242,28 @@ def test_output_slots_are_recycled_only_when_released():
     del view, field
     assert all(pool.is_free(s, 7) for s in pool._ring)
     assert not any(pool.is_free(s, 8) for s in pool._ring)         # another stream: never recycled there
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/marlnav_b200.h compiles as C99 (-Wall -Werror), every declared entry point links against
+    libmarlnav_b200.so, the struct sizes agree, and a stale struct is rejected -- from a C program,
+    the way a non-Python binding (cgo, JNI, ...) would see the library."""
+    import shutil
+    from marlnav_b200 import build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    lib = build.build()
+    exe = tmp_path / "abi_check"
+    src = os.path.join(ROOT, "tests", "c", "abi_check.c")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-o", str(exe), src, "-L" + os.path.dirname(lib),
+           "-lmarlnav_b200", "-Wl,-rpath," + os.path.dirname(lib)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "abi 4 ok" in run.stdout
+    # every function the header declares is referenced by the C program
+    header = open(os.path.join(ROOT, "include", "marlnav_b200.h")).read()
+    declared = set(re.findall(r"\b(marlnav_[a-z0-9_]+)\s*\(", header))
+    assert all(name in open(src).read() for name in declared)
