@@ -76,7 +76,7 @@ def ncu_traffic(A, O, B):
 
 def kernel_name(A, O, B):
     if A == 3 and O <= 6:
-        return "mn::step_team_kernel" if B <= 16384 else "mn::step_env_kernel"
+        return "mn::step_team_kernel" if B <= 32768 else "mn::step_env_kernel"
     return "mn::step_team_kernel" if (A, O) == (8, 16) else "mn::step_kernel"
 
 

@@ -83,3 +83,19 @@ def test_cuda_vs_stock_reference_teacher_forced(name):
     be = _backend(meta)
     checked, flips = gr.teacher_forced_vs_stock(name + " [cuda]", be, z, meta, be.e.num_agents, be.e.num_obstacles)
     assert checked >= 80 and flips <= 2
+
+
+def test_reference_traces_through_the_thread_per_env_kernel():
+    """The golden traces are small batches, which the library would run thread-per-agent: replay them in
+    a child process with MARLNAV_TEAM3_MAX_ENVS=0, i.e. through the thread-per-env kernel that steps
+    the 1M-env batches (the variable is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, MARLNAV_TEAM3_MAX_ENVS="0")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_golden.py"), "-q", "-x", "-m", "gpu",
+                          "-k", "reproduces or teacher_forced or constant_sampler", "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout and "failed" not in res.stdout

@@ -94,6 +94,16 @@ def test_triangle_3x3_free_running(oracle):
     assert ndone > 1000          # the reset path was really exercised
 
 
+def test_triangle_3x3_free_running_thread_per_env(oracle):
+    """Above 32 768 envs the team of 3 runs the thread-per-env kernel (the headline path at 1M envs):
+    240 free-running steps with thousands of resets, every tensor compared every 6th step."""
+    import marlnav_b200 as mb
+    p = mb.default_env_params(40000, 3, 3, sampling_style='policy', episode_len=100)
+    assert mb.Env(dict(p, seed=1)).launch_info()[3] == 32
+    ndone = _run_free(p, oracle, steps=240, check_every=6)
+    assert ndone > 40000
+
+
 def test_triangle_3x3_wide_turns(oracle):
     import marlnav_b200 as mb
     _run_free(mb.default_env_params(1024, 3, 3, sampling_style='policy'), oracle, steps=64, angle=4.0)
@@ -218,7 +228,7 @@ def test_noisy_agents_free_running(oracle, make):
     if make == "tri_small":
         p = mb.default_env_params(777, 3, 3, sampling_style='policy', episode_len=40)
     elif make == "tri_large":
-        p = mb.default_env_params(20000, 3, 3, sampling_style='policy', episode_len=40)
+        p = mb.default_env_params(40000, 3, 3, sampling_style='policy', episode_len=40)
     elif make == "ring_8x16":
         p = mb.template_env_params(301, 8, 16, episode_len=40)
     else:
@@ -312,7 +322,7 @@ def test_step_outputs_are_fresh_until_released(oracle):
     assert len(env._ring) <= n_slots + 1 and len(ptrs) <= n_slots + 1
 
 
-@pytest.mark.parametrize("A,O,B", [(3, 3, 3000), (3, 3, 20000), (8, 16, 300)])
+@pytest.mark.parametrize("A,O,B", [(3, 3, 3000), (3, 3, 40000), (8, 16, 300)])
 def test_zero_clamp_bounds(oracle, A, O, B):
     """min_accel = 0 / min_speed = 0: torch.clamp's `(a < b) ? b : a` keeps a -0 against a +0 bound (a
     two-FMNMX clamp would not; measured no faster and not used)."""

@@ -290,9 +290,10 @@ def test_sharded_rollout_equals_single_process():
         assert bool(whole['done'].any())
 
 
-@pytest.mark.parametrize("B", [1, 5, 33, 1000, 16385, 20001])
+@pytest.mark.parametrize("B", [1, 5, 33, 1000, 16385, 32769, 40001])
 def test_fused_actor_step_ragged_batches(B):
-    """Batches that are not a multiple of the tile (8 envs per warp thread-per-agent, 32 thread-per-env)
+    """Batches that are not a multiple of the tile (8 envs per warp thread-per-agent up to 32 768 envs, 32
+    thread-per-env above)
     through the fused {actor -> step} launch == the two-launch route."""
     import marlnav_b200 as mb
     A, O, T = 3, 3, 24
