@@ -392,6 +392,27 @@ class Env(object):
         self._io, self._io_tensors = (io, keep) if keep else (None, None)
         self.__dict__.pop('_call_cache', None)
 
+    def fuse_io_tensors(self, obs_mean=None, obs_scale=None, act_mean=None, act_scale=None):
+        """``fuse_io`` from the tensors an existing ``ObsNormalizer`` / ``ActionScaler`` already holds
+        (``.mean`` and one row of ``.scale_tensor``, utils.py:523-528,539-544): the kernel then divides /
+        multiplies by exactly the values the reference's callables would."""
+        dev = self.device
+        io = _lib.IoTransform()
+        keep = []
+        cvt = lambda t, n: torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1)[:n].to(dev).contiguous()
+        if obs_mean is not None:
+            mean, scale = cvt(obs_mean, self.obs_size), cvt(obs_scale, self.obs_size)
+            if mean.numel() != self.obs_size or scale.numel() != self.obs_size:
+                raise _lib.MarlnavError(f"normalizer needs {self.obs_size} entries")
+            io.obs_mean, io.obs_scale = mean.data_ptr(), scale.data_ptr()
+            keep += [mean, scale]
+        if act_mean is not None:
+            mean, scale = cvt(act_mean, 2), cvt(act_scale, 2)
+            io.act_mean, io.act_scale = mean.data_ptr(), scale.data_ptr()
+            keep += [mean, scale]
+        self._io, self._io_tensors = (io, keep) if keep else (None, None)
+        self.__dict__.pop('_call_cache', None)
+
     def observations_fused(self):
         """(B,A,S) observation buffer of the current states (one kernel launch)."""
         B, A = self.num_parallel, self.num_agents

@@ -355,3 +355,62 @@ class StepGraph:
         self.graph.replay()
         self.env._reset_counter += self.steps          # host mirror of the device word
         return self.outputs
+
+
+class MappoRollout:
+    """``MAPPO.get_data`` (models.py:106-129) for the reference's own learner object, on the device:
+    ``MappoRollout(mappo).attach()`` replaces ``mappo.get_data`` so that the training loop of
+    marlnav/__main__.py:21-27 (``get_data`` -> ``train_actor`` -> ``train_critic``) runs unchanged, but the
+    rollout is {fused actor sample -> fused step} x buffer_len with the critic beside it -- one CUDA-graph
+    launch -- and the backward return scan (models.py:131-148) one kernel.
+
+    ``mappo`` needs what the reference's ``MAPPO`` has: ``env`` (a ``marlnav_b200.Env``), ``actor``,
+    ``critic``, ``_normalize`` / ``_scale_up`` (the reference's ``ObsNormalizer`` / ``ActionScaler``),
+    ``buffer_len``, ``gamma``, ``num_parallel``, ``num_agents``, ``action_size``, ``_logs``,
+    ``_update_epi_stats``.  After ``get_data()`` ``mappo.buffer`` holds, per step, the reference's
+    ``[obs (B,A,S), actions (B,A,2), log_probs (B*A), values (B,1), returns (B) float64, done (B)]`` --
+    views of the rollout's (T, ...) device buffers, valid until the next ``get_data()``.
+
+    Differences from the reference's loop: the exploration noise is an addressed Philox stream
+    instead of torch's global generator (same distribution), and nothing is printed per step."""
+
+    def __init__(self, mappo, use_graph=True, seed=None):
+        env = mappo.env
+        self.mappo, self.env, self.use_graph = mappo, env, bool(use_graph)
+        norm, scal = mappo._normalize, mappo._scale_up
+        env.fuse_io_tensors(norm.mean, norm.scale_tensor.reshape(-1, env.obs_size)[0],
+                            scal.mean, scal.scale_tensor.reshape(-1, 2)[0])
+        self.actor = FusedActor(mappo.actor, device=env.device, seed=seed)
+        self.critic = FusedCritic(mappo.critic, device=env.device)
+        self.graph = None
+
+    def attach(self):
+        self.mappo.get_data = self.get_data
+        return self
+
+    @torch.no_grad()
+    def get_data(self):
+        m, env = self.mappo, self.env
+        T, B, A = int(m.buffer_len), env.num_parallel, env.num_agents
+        self.actor.refresh(m.actor)                       # the optimisers stepped since the last rollout
+        self.critic.refresh(m.critic)
+        if self.use_graph:
+            if self.graph is None:
+                self.graph = RolloutGraph(env, self.actor, T, critic=self.critic)
+            buf = self.graph.replay()
+        else:
+            buf = collect_rollout(env, self.actor, T, critic=self.critic)
+        # models.py:131-148: discounted returns, normalised over the whole buffer
+        ret = discounted_returns(buf['rewards'], buf['done'], float(m.gamma))
+        std, mean_rew = torch.std_mean(ret.reshape(-1))
+        ret = (ret - mean_rew) / (std + 1e-12)
+        acts = buf['actions'].view(T, B, A, int(m.action_size))
+        m.obs = buf['last_obs']
+        m.buffer = [[buf['obs'][t], acts[t], buf['log_probs'][t], buf['values'][t], ret[t], buf['done'][t]]
+                    for t in range(T)]
+        m._mean_rew = mean_rew
+        m._logs['mean_rews'] += [mean_rew.item()]
+        m._update_epi_stats()                             # models.py:151-158
+        if m._mean_rew > m._max_rew:                      # models.py:127-129, literally
+            torch.save(m.actor.state_dict(), m._actor_path)
+            torch.save(m.critic.state_dict(), m._critic_path)

@@ -73,7 +73,10 @@ def run_check_rews(env_cls, sn):
                 stats=[int(env._num_trunc), int(env._num_col), int(env._num_tar)])
 
 
-def run_training_rollout(env_cls, buffer_len):
+def run_training_rollout(env_cls, buffer_len, fast=False):
+    """fast=True: the reference's MAPPO object with marlnav_b200.MappoRollout attached -- ONE added line
+    (`mb.MappoRollout(mappo).attach()`); get_data / train_actor / train_critic are then called as
+    marlnav/__main__.py:21-27 does."""
     args = ref_args(num_parallel=1024, sampling_style='policy', buffer_len=buffer_len, batch_size=buffer_len,
                     num_total=1024 * buffer_len)
     U.set_all_seeds(0)
@@ -85,13 +88,16 @@ def run_training_rollout(env_cls, buffer_len):
         mappo = M.MAPPO(params['model'], env)
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):        # the reference prints every step
+            if fast:
+                mb.MappoRollout(mappo, seed=0).attach()
+                mappo.get_data(); torch.cuda.synchronize()      # builds the CUDA graph (one-off)
             t0 = time.perf_counter(); mappo.get_data(); torch.cuda.synchronize(); t_roll = time.perf_counter() - t0
             t0 = time.perf_counter(); mappo.train_actor(); mappo.train_critic(); torch.cuda.synchronize()
             t_train = time.perf_counter() - t0
     finally:
         os.chdir(cwd)
     logs = mappo._logs
-    return dict(mode=f"MAPPO rollout -np 1024 -bl {buffer_len}", env=env_cls.__module__,
+    return dict(mode=f"MAPPO rollout -np 1024 -bl {buffer_len}" + (" + MappoRollout.attach()" if fast else ""), env=env_cls.__module__,
                 rollout_seconds=round(t_roll, 3), env_steps_per_sec=round(1024 * buffer_len / t_roll),
                 train_seconds=round(t_train, 3), mean_rew=logs['mean_rews'][-1],
                 epi_stats={k: v[-1] for k, v in logs['epi_stats'].items()},
@@ -104,4 +110,5 @@ if __name__ == "__main__":
         print(json.dumps(run_check_rews(mb.Env, sn)), flush=True)
     print(json.dumps(run_check_rews(E.Env, 0)), flush=True)            # reference Env on the same GPU
     print(json.dumps(run_training_rollout(mb.Env, 1000)), flush=True)
+    print(json.dumps(run_training_rollout(mb.Env, 1000, fast=True)), flush=True)
     print(json.dumps(run_training_rollout(E.Env, 100)), flush=True)    # reference Env: 10x shorter rollout
