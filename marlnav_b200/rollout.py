@@ -406,8 +406,9 @@ class MappoRollout:
         ret = (ret - mean_rew) / (std + 1e-12)
         acts = buf['actions'].view(T, B, A, int(m.action_size))
         m.obs = buf['last_obs']
-        m.buffer = [[buf['obs'][t], acts[t], buf['log_probs'][t], buf['values'][t], ret[t], buf['done'][t]]
-                    for t in range(T)]
+        # (unbind: the T views of each buffer in one call instead of T Python indexing operations)
+        m.buffer = [list(row) for row in zip(buf['obs'].unbind(0), acts.unbind(0), buf['log_probs'].unbind(0),
+                                             buf['values'].unbind(0), ret.unbind(0), buf['done'].unbind(0))]
         m._mean_rew = mean_rew
         m._logs['mean_rews'] += [mean_rew.item()]
         m._update_epi_stats()                             # models.py:151-158
