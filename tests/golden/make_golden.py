@@ -37,6 +37,7 @@ torch.set_num_threads(4)
 env_mod, utils_mod = refload.load()
 
 SNAP_EVERY = 20
+FACTORS = ('risk_factor', 'distance_factor', 'heading_factor', 'target_factor', 'soft_factor', 'bond_factor')
 
 
 def actions_for(B, A, steps, seed, angle=0.2, accel=0.5):
@@ -118,6 +119,9 @@ def random_case(name, B, A, O, steps, seed, act_seed, patched, template=None, an
     arr['actions'] = np.stack([a.numpy() for a in acts])
     meta = dict(B=B, A=A, O=O, steps=steps, seed=seed, act_seed=act_seed, angle=angle,
                 episode_len=over.get('episode_len', 200))
+    for k in FACTORS:                                # non-default reward factors travel with the trace
+        if k in over:
+            meta[k] = float(over[k])
     if template is not None:
         meta['template'] = np.asarray(template, np.float32)
     save(name, meta, arr)
@@ -307,6 +311,18 @@ def noisy_case(name, B, steps, seed, act_seed, patched):
     save(name, dict(B=B, A=3, O=3, steps=steps, seed=seed, act_seed=act_seed, angle=0.2, episode_len=60, noisy=1), arr)
 
 
+def factor_cases():
+    """The CLI defaults multiply the risk and the distance score by 0 (`-rf 0 -df 0`, __main__.py:89-92), so
+    the default traces cannot see an error in them: the same free-running traces with every reward
+    factor non-zero, (3,3) and the (8,16) ring."""
+    fac = dict(risk_factor=37.5, distance_factor=123.0, heading_factor=410.0, target_factor=650.0,
+               soft_factor=275.0, bond_factor=7.25)
+    random_case('patched_tri_3x3_factors', 40, 3, 3, 140, seed=9, act_seed=5, patched=True, episode_len=45, **fac)
+    random_case('patched_ring_8x16_factors', 8, 8, 16, 50, seed=10, act_seed=6, patched=True,
+                template=orc.ring_template(8), episode_len=30, **fac)
+    random_case('stock_tri_3x3_factors', 40, 3, 3, 80, seed=9, act_seed=5, patched=False, episode_len=45, **fac)
+
+
 def quirk_case(name):
     """delayed target termination, collision+target,
     truncation -- 4 hand-placed envs, stock reference, constant action [0, -10]."""
@@ -338,6 +354,8 @@ if __name__ == '__main__':
             snm1_case('stock_rc_snm1', 0, patched=False)
         if 'models' in only:
             models_case('ref_models')
+        if 'factors' in only:
+            factor_cases()
         if 'noisy' in only:
             noisy_case('patched_noisy_3x3', 24, 200, seed=11, act_seed=77, patched=True)
             noisy_case('stock_noisy_3x3', 24, 80, seed=11, act_seed=77, patched=False)
@@ -362,3 +380,4 @@ if __name__ == '__main__':
     models_case('ref_models')
     noisy_case('patched_noisy_3x3', 24, 200, seed=11, act_seed=77, patched=True)
     noisy_case('stock_noisy_3x3', 24, 80, seed=11, act_seed=77, patched=False)
+    factor_cases()

@@ -27,6 +27,9 @@ def params_for(meta, make_default, make_template, **over):
     else:
         p = make_default(B, A, O, sampling_style="policy")
     p["episode_len"] = int(meta.get("episode_len", 200))
+    for k in ("risk_factor", "distance_factor", "heading_factor", "target_factor", "soft_factor", "bond_factor"):
+        if k in meta:
+            p[k] = float(meta[k])                  # traces recorded with non-default reward factors
     if int(meta.get("noisy", 0)):
         p["init"]["noisy_ags"] = True            # utils.py:25 switched on
     p.update(over)
@@ -177,7 +180,8 @@ def teacher_forced_vs_stock(name, backend, z, meta, A, O):
             ta = np.abs(want[keep][:, :, 0])
             assert (np.abs(ta - np.float32(np.pi / 8)) < 1e-5).any(axis=1).all(), f"{name} step {t}: reward off"
             # each flip moves the reward by heading_factor / A
-            assert (np.abs(dr[bad] / (500.0 / A) - np.round(dr[bad] / (500.0 / A))) < 1e-3).all(), f"{name} step {t}: reward off"
+            unit = float(meta.get("heading_factor", 500.0)) / A
+            assert (np.abs(dr[bad] / unit - np.round(dr[bad] / unit)) < 1e-3).all(), f"{name} step {t}: reward off"
             flips += int(bad.sum())
         checked += rew.size
     return checked, flips

@@ -9,7 +9,7 @@ import golden_replay as gr
 pytestmark = pytest.mark.gpu
 
 NAMES = ["patched_tri_3x3", "patched_tri_3x3_wide", "patched_ring_8x16", "patched_ring_4x2", "patched_ring_9x5",
-         "patched_noisy_3x3"]
+         "patched_noisy_3x3", "patched_tri_3x3_factors", "patched_ring_8x16_factors"]
 
 
 def _backend(meta, **over):
@@ -74,7 +74,7 @@ def test_cuda_vs_stock_constant_sampler_scenario():
     assert be.stats() == tuple(int(v) for v in z["stats"])
 
 
-@pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16", "stock_noisy_3x3"])
+@pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16", "stock_noisy_3x3", "stock_tri_3x3_factors"])
 def test_cuda_vs_stock_reference_teacher_forced(name):
     """Stock reference (MKL trig) per-step snapshots replayed on the GPU: flags / reset decisions
     bit-exact; states, distances and rewards within 1e-5 (north-star tolerance); angles within 1e-5

@@ -331,3 +331,32 @@ def test_zero_clamp_bounds(oracle, A, O, B):
     p.update(min_accel=0.0, min_speed=0.0)
     ndone = _run_free(p, oracle, steps=80, check_every=4)
     assert ndone > 0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_parameters(oracle, seed):
+    """Every reward factor non-zero (the defaults multiply the risk and distance scores by 0, which would
+    hide an error in them), random speed / acceleration limits, episode lengths, obstacle boxes and
+    geometry thresholds, across all four step kernels: thread-per-env and thread-per-agent team of 3,
+    the (8,16) team kernel and the generic kernel."""
+    import marlnav_b200 as mb
+    rng = np.random.default_rng(100 + seed)
+    A, O, B = [(3, 3, 40000), (3, 3, 900), (8, 16, 320), (3, 5, 35000), (5, 4, 300), (3, 1, 1500), (8, 16, 64), (2, 2, 257)][seed]
+    p = mb.default_env_params(B, A, O, sampling_style='policy') if A == 3 else mb.template_env_params(B, A, O)
+    p.update(risk_factor=float(rng.uniform(1, 300)), distance_factor=float(rng.uniform(1, 300)),
+             heading_factor=float(rng.uniform(1, 800)), target_factor=float(rng.uniform(1, 800)),
+             soft_factor=float(rng.uniform(1, 800)), bond_factor=float(rng.uniform(0.1, 50)),
+             min_speed=float(rng.uniform(0.5, 4)), max_speed=float(rng.uniform(6, 14)),
+             min_accel=float(-rng.uniform(0.1, 1)), max_accel=float(rng.uniform(0.1, 1)),
+             episode_len=int(rng.integers(8, 70)))
+    p['init'].update(obst_min_x=float(rng.uniform(250, 500)), obst_max_x=float(rng.uniform(700, 1200)),
+                     obst_min_y=float(rng.uniform(100, 300)), obst_max_y=float(rng.uniform(450, 700)))
+    geometry = dict(ob_risk_dist=float(rng.uniform(55, 90)), ag_risk_dist=float(rng.uniform(10, 35)),
+                    ob_coll_dist=float(rng.uniform(30, 55)), ag_coll_dist=float(rng.uniform(2, 9)),
+                    agents_min_d=float(rng.uniform(20, 35)), agents_max_d=float(rng.uniform(42, 60)),
+                    target_radius=float(rng.uniform(20, 60)), ideal_dist=float(rng.uniform(30, 50)))
+    if seed % 2:                                     # every other case also leaves the compiled-in division profile
+        geometry.update(init_dist=float(rng.uniform(800, 1600)), max_at_prop_d=float(rng.integers(1, A)),
+                        bond_sharpness=float(rng.uniform(0.5, 4)))
+    ndone = _run_free_with_geometry(p, oracle, 90, geometry, seed=seed)
+    assert ndone > 0

@@ -16,7 +16,7 @@ import golden_replay as gr
 from helpers import assert_bits_equal
 
 PATCHED_RANDOM = ["patched_tri_3x3", "patched_tri_3x3_wide", "patched_ring_8x16", "patched_ring_4x2",
-                  "patched_ring_9x5", "patched_noisy_3x3"]
+                  "patched_ring_9x5", "patched_noisy_3x3", "patched_tri_3x3_factors", "patched_ring_8x16_factors"]
 
 
 def _oracle_backend(oracle, meta, **over):
@@ -95,7 +95,7 @@ def test_torch_port_reproduces_stock_reference(oracle, name):
         pytest.skip("host torch CPU trig differs from the golden-generating host; ran for crashes only")
 
 
-@pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16", "stock_noisy_3x3"])
+@pytest.mark.parametrize("name", ["stock_tri_3x3", "stock_ring_8x16", "stock_noisy_3x3", "stock_tri_3x3_factors"])
 def test_c_oracle_vs_stock_reference_teacher_forced(oracle, name):
     """Identical pre-step states and actions into the oracle and the STOCK reference (MKL trig):
     terminal flags and reset decisions bit-exact, states/distances/rewards within 1e-5,
