@@ -166,13 +166,14 @@ def test_sharded_equals_single(oracle):
     assert torch.equal(tot, e_full.episode_stats)
 
 
-def test_fused_normalizer_and_scaler(oracle):
+@pytest.mark.parametrize("B,A,O", [(777, 3, 3), (40000, 3, 3), (300, 8, 16), (200, 4, 2)])
+def test_fused_normalizer_and_scaler(oracle, B, A, O):
     """fuse_io(): ObsNormalizer (utils.py:519-532) and ActionScaler (utils.py:535-547) folded
-    into the kernel must equal applying them around the oracle step, bit for bit."""
+    into the kernel must equal applying them around the oracle step, bit for bit -- in the NORM builds
+    of all four step kernels (thread-per-agent and thread-per-env team of 3, (8,16), generic)."""
     import math
     import marlnav_b200 as mb
-    B, A, O = 777, 3, 3
-    params = mb.default_env_params(B, A, O, sampling_style='policy')
+    params = mb.default_env_params(B, A, O, sampling_style='policy') if A == 3 else mb.template_env_params(B, A, O)
     env = _mk(params, 9)
     oe = oracle.OracleEnv(cpu_params(params), seed=9)
     max_d = math.sqrt(1500.0 ** 2 + 750.0 ** 2)
@@ -198,13 +199,35 @@ def test_fused_normalizer_and_scaler(oracle):
     assert_bits_equal("states", env.states.cpu().numpy(), oe.states)
 
 
-def test_host_stepper_matches_device_step(oracle):
-    """marlnav_step_host_f32 (pinned host in/out) == the device-resident step."""
+@pytest.mark.parametrize("B,A,O", [(500, 3, 3), (40000, 3, 3), (300, 8, 16), (200, 5, 3)])
+def test_observations_after_a_step_equal_the_steps_observations(oracle, B, A, O):
+    """Env.observations() (environment.py:139-180, its own kernel) on the state a step left behind ==
+    the (post-reset) observations that step returned, and == the oracle's."""
     import marlnav_b200 as mb
-    params = mb.default_env_params(2048, 3, 3, sampling_style='policy')
+    p = mb.default_env_params(B, A, O, sampling_style='policy', episode_len=12) if A == 3 else mb.template_env_params(B, A, O, episode_len=12)
+    env = _mk(p, 2)
+    oe = oracle.OracleEnv(cpu_params(p), seed=2)
+    pool = action_pool(B, A)
+    for t in range(30):
+        obs, _, term, trunc = env.step_fused(pool[t % 8].cuda())
+        oe.step_fused(pool[t % 8].numpy())
+        if t % 6 == 5:
+            again = env.observations_fused()
+            assert torch.equal(again, obs), t
+            assert_bits_equal(f"step {t} observations()", again.cpu().numpy(), oe.observations_fused())
+            fields = env.observations()
+            assert torch.equal(torch.cat(list(fields), dim=2), again)
+
+
+@pytest.mark.parametrize("B", [2048, 70001])
+def test_host_stepper_matches_device_step(oracle, B):
+    """marlnav_step_host_f32 (pinned host in/out) == the device-resident step; 70 001 envs go through the
+    chunked pipeline (two chunks on three streams, the second with its env-id offset and a ragged tail)."""
+    import marlnav_b200 as mb
+    params = mb.default_env_params(B, 3, 3, sampling_style='policy', episode_len=15)
     e1, e2 = _mk(params, 4), _mk(params, 4)
     hs = mb.HostStepper(e2)
-    pool = action_pool(2048, 3)
+    pool = action_pool(B, 3)
     for t in range(40):
         act = pool[t % len(pool)]
         obs, rew, term, trunc = e1.step_fused(act.cuda())
