@@ -383,3 +383,19 @@ def test_randomised_parameters(oracle, seed):
                         bond_sharpness=float(rng.uniform(0.5, 4)))
     ndone = _run_free_with_geometry(p, oracle, 90, geometry, seed=seed)
     assert ndone > 0
+
+
+@pytest.mark.parametrize("A,O,B", [(3, 3, 600), (3, 3, 36000), (8, 16, 200), (4, 2, 300)])
+def test_template_with_negative_values_and_negative_zero(oracle, A, O, B):
+    """An agent template with negative coordinates and a -0.0 heading component: the "+0 wash" shortcut
+    of the default reset source does not apply (MARLNAV_RESET_TMPL_NONNEG is not set), so the kernels
+    must evaluate the literal blend (1-m)*old + m*new for every env -- including the sign of zeros."""
+    import marlnav_b200 as mb
+    tmpl = mb.ring_template(A, cx=-30.0, cy=375.0)
+    for i, row in enumerate(tmpl):
+        row[2], row[3] = (1.0, -0.0) if i % 2 else (1.0, 0.0)
+    p = mb.template_env_params(B, A, O, agent_template=tmpl, episode_len=20)
+    env = _mk(p, 3)
+    assert not env._tmpl_nonneg
+    ndone = _run_free(p, oracle, steps=70, seed=3, check_every=3)
+    assert ndone > B
