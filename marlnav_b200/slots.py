@@ -72,6 +72,8 @@ class OutputSlots:
             if self.is_free(slot, stream):
                 return slot
         slot = self._new(stream)
+        if _storage_use_count is None:                 # nothing could ever be recycled: do not hoard
+            return slot
         if len(ring) < self.MAX_SLOTS and self._bytes + slot['nbytes'] <= self.MAX_BYTES:
             ring.append(slot)
             self._bytes += slot['nbytes']
