@@ -219,10 +219,11 @@ def test_observations_after_a_step_equal_the_steps_observations(oracle, B, A, O)
             assert torch.equal(torch.cat(list(fields), dim=2), again)
 
 
-@pytest.mark.parametrize("B", [2048, 70001])
+@pytest.mark.parametrize("B", [2048, 70001, 140001])
 def test_host_stepper_matches_device_step(oracle, B):
     """marlnav_step_host_f32 (pinned host in/out) == the device-resident step; 70 001 envs go through the
-    chunked pipeline (two chunks on three streams, the second with its env-id offset and a ragged tail)."""
+    chunked pipeline (two chunks on three streams, the second with its env-id offset and a ragged tail),
+    140 001 through the ramped one (chunks of 8 704, 17 536, 3 x 35 072 and a ragged 8 545 envs)."""
     import marlnav_b200 as mb
     params = mb.default_env_params(B, 3, 3, sampling_style='policy', episode_len=15)
     e1, e2 = _mk(params, 4), _mk(params, 4)
