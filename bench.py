@@ -81,12 +81,19 @@ def kernel_name(A, O, B):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons through NVML during the timed region."""
+    """Samples SM clock + throttle reasons through NVML during the timed region.
+
+    The thread is created and parked BEFORE the region and released by arm() only once every step
+    of the region has been enqueued: the samples are taken while the GPU executes those steps, and
+    neither a thread start-up nor an NVML call (driver locks, the GIL) competes with the launch loop
+    -- at the driver's --steps 20 the region is 1.3 ms long and a first sample taken inside the
+    loop cost 3-5 % of it."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self._go = threading.Event()
         self._h = None
         try:
             import pynvml
@@ -107,6 +114,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
+        self._go.wait()
         while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
@@ -119,10 +127,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.004 if self.samples else 0.0002)    # (a failed first call is retried at once)
+
+    def arm(self):
+        self._go.set()
 
     def stop(self):
         self._halt.set()
+        self._go.set()
         self.join(timeout=1.0)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
@@ -408,15 +420,20 @@ def run_ours(args):
     # ---- headline: the reference-facing Env.step (fresh output tensors every step, models.py:121)
     for i in range(W):
         env.step(pool[i % 16])
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                  # parked until arm()
+    legacy_sampler = os.environ.get("MARLNAV_BENCH_SAMPLER", "") == "legacy"     # A/B of the note above
     barrier()
     stats0 = env.episode_stats.clone()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    torch.cuda.synchronize()
+    if legacy_sampler:
+        sampler.arm()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
         env.step(pool[i % 16])
     e1.record()
+    sampler.arm()                                    # the GPU is still executing the K steps
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
